@@ -1,0 +1,201 @@
+/*
+ * scipnp.h -- C ABI of libscipnp.so, the B200 (sm_100a) GAP/ADMM-TV engine for
+ * snapshot compressive imaging.
+ *
+ * This is the drop-in boundary for the iterative hot path of the reference's
+ * PnP_SCI/python.  Every entry point states the reference
+ * interface it replaces (file:line under /root/reference/PnP_SCI/python).
+ *
+ * Conventions
+ *   - plain C: pointers, ints, floats; no C++ or torch types.
+ *   - every function returns 0 on success or a negative SCIPNP_E* code; the
+ *     message of the last failure on the calling thread is scipnp_last_error().
+ *   - "dev" pointers are device pointers on the current CUDA device; "host"
+ *     pointers are ordinary (pageable or pinned) host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls
+ *     are asynchronous on that stream unless stated otherwise.
+ *   - array layout is the reference's logical layout, C-contiguous float32:
+ *       frames / masks  x, Phi : [B][H][W][C]   (channel-last, C = Cr)
+ *       measurements    y, y1, Phi_sum : [B][H][W]
+ *     `B` batches independent measurements.  `phi_batched` = 0 shares one
+ *     Phi / Phi_sum ([H][W][C] / [H][W]) between all B measurements, 1 gives
+ *     every measurement its own.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     returns SCIPNP_ECUDA.
+ */
+#ifndef SCIPNP_H
+#define SCIPNP_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCIPNP_OK        0
+#define SCIPNP_EINVAL   -1   /* bad argument                                   */
+#define SCIPNP_ECUDA    -2   /* CUDA runtime error (message has the detail)    */
+#define SCIPNP_ENOMEM   -3   /* device or host allocation failed               */
+#define SCIPNP_ESTATE   -4   /* call not valid in the handle's current state   */
+
+/* library ------------------------------------------------------------------ */
+int         scipnp_version(void);            /* 10000*major + 100*minor + patch */
+const char *scipnp_last_error(void);
+int         scipnp_device_count(void);       /* 0 when no usable CUDA device    */
+long long   scipnp_launch_count(void);       /* kernels launched by this process */
+
+/* R1  utils.A_  (utils.py:10-15):  y[b,h,w] = sum_c x[b,h,w,c]*Phi[.,h,w,c]     */
+int scipnp_A(const float *x_dev, const float *Phi_dev, float *y_dev,
+             int B, int H, int W, int C, int phi_batched, void *stream);
+
+/* R2  utils.At_ (utils.py:17-26):  x[b,h,w,c] = y[b,h,w]*Phi[.,h,w,c]           */
+int scipnp_At(const float *y_dev, const float *Phi_dev, float *x_dev,
+              int B, int H, int W, int C, int phi_batched, void *stream);
+
+/* R3  mask_sum  (pnp_sci_algo.py:491-492): sum_c Phi, zeros replaced by 1       */
+int scipnp_phi_sum(const float *Phi_dev, float *Phi_sum_dev,
+                   int B, int H, int W, int C, void *stream);
+
+/* R4  Euclidean projection of gap_denoise (pnp_sci_algo.py:640-645):
+ *        yb = A(x);  accelerate: y1 += y-yb; x += lambda*At((y1-yb)/Phi_sum)
+ *                    else      :             x += lambda*At((y -yb)/Phi_sum)
+ *     x_in/x_out and y1_in/y1_out may alias (pointwise).  y1 pointers may be
+ *     NULL when accelerate == 0.                                                */
+int scipnp_gap_project(const float *x_in, float *x_out,
+                       const float *y1_in, float *y1_out,
+                       const float *y, const float *Phi, const float *Phi_sum,
+                       float lambda, int accelerate,
+                       int B, int H, int W, int C, int phi_batched, void *stream);
+
+/* R5  Euclidean projection of admm_denoise (pnp_sci_algo.py:808-809,812):
+ *        u = theta+b; x = u + lambda*At((y-A(u))/(Phi_sum+gamma)); f = x-b
+ *     writes x (the solver's return value) and f (the TV input).               */
+int scipnp_admm_project(const float *theta, const float *b, float *x, float *f,
+                        const float *y, const float *Phi, const float *Phi_sum,
+                        float lambda, float gamma,
+                        int B, int H, int W, int C, int phi_batched, void *stream);
+
+/* R5  multiplier update (pnp_sci_algo.py:836):  b = b - (x - theta)            */
+int scipnp_admm_dual_update(float *b, const float *x, const float *theta,
+                            size_t n, void *stream);
+
+/* R6  skimage.restoration.denoise_tv_chambolle(image, weight, eps, n_iter_max,
+ *     multichannel=True)  (call sites pnp_sci_algo.py:164,409,650,812): every
+ *     (b, c) slice is an independent 2-D ROF problem, tau = 1/4, energy-based
+ *     early stop evaluated on the device per slice exactly as the reference.
+ *     `in` and `out` must not alias.  `workspace` holds the dual field
+ *     (scipnp_tv_workspace_bytes).  Optional outputs (may be NULL):
+ *       n_exec_dev  int   [B*C]            iterations executed per slice
+ *       energy_dev  double[B*C][energy_cap] E_i per slice (unused entries NaN)  */
+size_t scipnp_tv_workspace_bytes(int B, int H, int W, int C);
+int scipnp_tv_chambolle(const float *in, float *out, double weight, double eps,
+                        int n_iter_max, int B, int H, int W, int C,
+                        void *workspace, size_t workspace_bytes,
+                        int *n_exec_dev, double *energy_dev, int energy_cap,
+                        void *stream);
+
+/* R10 utils.psnr (utils.py:28-36): accumulates sum((a-b)^2) into *sum_dev
+ *     (double, device; the caller zeroes it).  psnr = 10*log10(n/sum).         */
+int scipnp_sq_err(const float *a, const float *b, size_t n, double *sum_dev,
+                  void *stream);
+
+/* One whole outer GAP-TV iteration, projection + TV in a single pass over HBM
+ * (replaces pnp_sci_algo.py:640-650 for denoiser='tv', tvm='tv_chambolle').
+ * Ping-pong: reads x_in / y1_in, writes x_out / y1_out (must not alias).
+ * `flags_dev` (int, >= 1 entry, may be NULL): set to nonzero when the energy
+ * criterion of the reference would have stopped some slice before n_iter_max;
+ * the caller then repeats the iteration with scipnp_gap_project +
+ * scipnp_tv_chambolle (the solver below does this by itself).                  */
+size_t scipnp_gap_tv_workspace_bytes(int B, int H, int W, int C, int tv_iter_max);
+int scipnp_gap_tv_fused(const float *x_in, float *x_out,
+                        const float *y1_in, float *y1_out,
+                        const float *y, const float *Phi, const float *Phi_sum,
+                        float lambda, int accelerate, double tv_weight, double tv_eps,
+                        int tv_iter_max, int B, int H, int W, int C, int phi_batched,
+                        void *workspace, size_t workspace_bytes, int *flags_dev,
+                        void *stream);
+
+/* R8  Bayer sub-lattice (pnp_sci_algo.py:99,116-137,255-257): split a
+ *     [H][W][C] mosaic stack into 4 half-resolution stacks [4][H/2][W/2][C]
+ *     (order (0,0),(0,1),(1,0),(1,1)) and back.  C = 1 handles [H][W] planes.   */
+int scipnp_bayer_split(const float *full, float *quad, int H, int W, int C, void *stream);
+int scipnp_bayer_merge(const float *quad, float *full, int H, int W, int C, void *stream);
+
+/* R9  CASSI dispersion (DeSCI/test_desci_cassi.m:53-62): expand a 2-D coded
+ *     aperture M[H][W] into the shifted stack Phi[H][W+(C-1)*step][C],
+ *     Phi[h, w+step*k, k] = M[h, w].                                            */
+int scipnp_cassi_shift_mask(const float *mask2d, float *Phi, int H, int W, int C,
+                            int step, void *stream);
+
+/* --------------------------------------------------------------------------
+ * Persistent solver: R4 gap_denoise / R5 admm_denoise with denoiser='tv'
+ * (pnp_sci_algo.py:536-706, 708-864).  All state stays in HBM for the whole
+ * run; only psnr_all comes back per iteration.
+ * -------------------------------------------------------------------------- */
+typedef struct scipnp_solver scipnp_solver;
+
+typedef struct scipnp_params {
+    int   method;        /* 0 = GAP, 1 = ADMM                                   */
+    int   accelerate;    /* GAP only                                            */
+    float lambda;        /* _lambda                                             */
+    float gamma;         /* ADMM only                                           */
+    double tv_weight;    /* double: tau/weight is rounded once, as NumPy does   */
+    double tv_eps;       /* skimage default 2e-4                                */
+    int   tv_iter_max;
+    int   fused;         /* 1: one-pass fused iteration where available         */
+    int   B, H, W, C;
+    int   phi_batched;
+    int   halo_rows;     /* >0: this handle owns a row block of a taller scene;
+                            rows [0,halo) and [H-halo,H) are neighbour copies   */
+} scipnp_params;
+
+int scipnp_solver_create(const scipnp_params *p, scipnp_solver **out);
+int scipnp_solver_destroy(scipnp_solver *s);
+
+/* Load inputs (host or device pointers, cudaMemcpyDefault).  Phi_sum == NULL
+ * derives it from Phi (R3).  x0 == NULL starts from At(y) (pnp_sci_algo.py:
+ * 625-627, 793-794).  X_orig == NULL disables psnr_all.                        */
+int scipnp_solver_load(scipnp_solver *s, const float *y, const float *Phi,
+                       const float *Phi_sum, const float *x0, const float *X_orig,
+                       void *stream);
+
+/* Run `iters` outer iterations on `stream` (asynchronous).  psnr_all entries are
+ * appended to an internal device array read by scipnp_solver_psnr.             */
+int scipnp_solver_run(scipnp_solver *s, int iters, void *stream);
+
+/* Copy the current estimate (GAP: x after TV; ADMM: x before TV, as the
+ * reference returns) to a host or device buffer and synchronise the stream.    */
+int scipnp_solver_get_x(scipnp_solver *s, float *x_out, void *stream);
+/* psnr_all (utils.psnr of every iteration against X_orig), one value per
+ * (iteration, batch element): psnr_all_host[k*B + b].  *count receives the
+ * number of values available; at most `cap` are written.  _sqerr returns the
+ * underlying sums of squared errors instead (callers that pool batch elements,
+ * e.g. the four Bayer sub-lattices).                                           */
+int scipnp_solver_psnr(scipnp_solver *s, double *psnr_all_host, int cap, int *count,
+                       void *stream);
+int scipnp_solver_sqerr(scipnp_solver *s, double *sums_host, int cap, int *count,
+                        void *stream);
+/* Number of outer iterations that had to be redone on the exact path because
+ * the TV energy criterion fired (0 in the reference's parameter range).        */
+int scipnp_solver_refined_iters(scipnp_solver *s, int *count);
+/* Device pointers of the state, for callers that manage halos themselves.      */
+int scipnp_solver_state(scipnp_solver *s, float **x_cur, float **y1_cur);
+/* Kernel launches issued since this handle was created.                        */
+long long scipnp_solver_launch_count(scipnp_solver *s);
+/* 1 when the handle runs the one-pass fused iteration, 0 on the exact path.    */
+int scipnp_solver_uses_fused(scipnp_solver *s);
+
+/* Host-buffer one-call entries (what a ctypes / cffi binding of the reference
+ * would call in place of gap_denoise / admm_denoise).  Synchronous.  psnr_all
+ * must hold iters*B doubles when X_orig is given (may be NULL otherwise).      */
+int scipnp_gap_denoise_host(const float *y, const float *Phi, const float *x0,
+                            const float *X_orig, const scipnp_params *p, int iters,
+                            float *x_out, double *psnr_all, int *psnr_count);
+int scipnp_admm_denoise_host(const float *y, const float *Phi, const float *x0,
+                             const float *X_orig, const scipnp_params *p, int iters,
+                             float *x_out, double *psnr_all, int *psnr_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCIPNP_H */

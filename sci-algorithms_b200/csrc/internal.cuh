@@ -1,0 +1,43 @@
+// Cross-file internal declarations of libscipnp.
+#pragma once
+#include "common.cuh"
+
+namespace scipnp {
+
+enum { MODE_GAP_ACC = 0, MODE_GAP_PLAIN = 1, MODE_ADMM = 2 };
+
+// ops.cu
+int launch_project(int mode, const float* a_in, const float* b_in, float* x_out, float* f_out,
+                   const float* y1_in, float* y1_out, const float* y, const float* Phi,
+                   const float* Phi_sum, float lambda, float gamma, int B, int H, int W, int C,
+                   int phi_batched, cudaStream_t st);
+
+int launch_sq_err(const float* a, const float* b, size_t n_per_batch, int B, double* sums,
+                  cudaStream_t st);
+
+// tv_exact.cu
+size_t tv_workspace_bytes(int B, int H, int W, int C);
+int tv_chambolle_exact(const float* in, float* out, double weight, double eps, int T, int B, int H,
+                       int W, int C, void* workspace, size_t ws_bytes, int* n_exec_dev,
+                       double* energy_dev, int energy_cap, cudaStream_t st);
+
+// gap_tv_fused.cu
+struct FusedArgs {
+    const float* x_in;  float* x_out;
+    const float* y1_in; float* y1_out;
+    const float* y; const float* Phi; const float* Phi_sum;
+    // ADMM (mode == MODE_ADMM): x_in = theta, b_in/b_out multiplier, xproj_out = x (may be null)
+    const float* b_in; float* b_out; float* xproj_out;
+    float lambda, gamma;
+    double tv_weight, tv_eps;
+    int tv_iter_max;
+    int mode;
+    int B, H, W, C, phi_batched;
+    void* workspace; size_t workspace_bytes;
+    int* flag;                // set nonzero if the energy criterion would have fired
+};
+bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
+size_t fused_workspace_bytes(int B, int H, int W, int C, int tv_iter_max);
+int launch_fused(const FusedArgs& a, cudaStream_t st);
+
+}  // namespace scipnp

@@ -1,0 +1,346 @@
+// Persistent GAP-TV / ADMM-TV solver (R4 gap_denoise, R5 admm_denoise with
+// denoiser='tv'): every array of the reference's loop (pnp_sci_algo.py:638-650,
+// 805-836) lives in HBM for the whole reconstruction.
+//
+// Two execution paths, chosen by scipnp_params.fused:
+//   fused = 1  one kernel per outer iteration (gap_tv_fused.cu), state ping-pongs
+//              between two buffers.  The kernel cannot apply skimage's energy
+//              early stop (a global per-slice reduction per dual iteration), so
+//              it evaluates the criterion and raises a flag; if any iteration of
+//              a run raised it the run is rolled back to its snapshot and redone
+//              on the exact path, so results never depend on the path taken.
+//   fused = 0  exact path: projection kernel + per-iteration TV kernels.
+#include <math.h>
+#include <new>
+#include <vector>
+
+#include "internal.cuh"
+
+using namespace scipnp;
+
+namespace {
+constexpr int kPsnrCap = 1 << 16;
+}
+
+struct scipnp_solver {
+    scipnp_params p;
+    size_t n_frame = 0;   // B*H*W*C
+    size_t n_meas = 0;    // B*H*W
+    size_t n_phi = 0, n_phisum = 0;
+    // device buffers
+    float *xa = nullptr, *xb = nullptr;       // GAP: x ping-pong.  ADMM: theta ping-pong
+    float *y1a = nullptr, *y1b = nullptr;     // GAP accelerated
+    float *ba = nullptr, *bb = nullptr;       // ADMM multiplier ping-pong
+    float *xproj = nullptr, *fbuf = nullptr;  // ADMM x and TV input
+    float *y = nullptr, *Phi = nullptr, *PhiSum = nullptr, *Xorig = nullptr;
+    float *xsnap = nullptr, *y1snap = nullptr, *bsnap = nullptr;   // rollback copies (fused)
+    void* tvws = nullptr; size_t tvws_bytes = 0;
+    void* fws = nullptr; size_t fws_bytes = 0;
+    double* sqerr = nullptr;   // [kPsnrCap]
+    int* flags = nullptr;      // [1]
+    // host state
+    bool loaded = false, has_orig = false, use_fused = false;
+    int iters_done = 0, psnr_count = 0, refined = 0;
+    long long launches0 = 0;
+    std::vector<void*> owned;
+
+    float* x_cur() { return xa; }
+};
+
+static int dmalloc(scipnp_solver* s, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    s->owned.push_back(*p);
+    return SCIPNP_OK;
+}
+#define DM(ptr, count, type)                                                   \
+    do {                                                                       \
+        if (int e_ = dmalloc(s, (void**)&(ptr), (size_t)(count) * sizeof(type))) { \
+            scipnp_solver_destroy(s);                                          \
+            return e_;                                                         \
+        }                                                                      \
+    } while (0)
+
+extern "C" {
+
+int scipnp_solver_destroy(scipnp_solver* s) {
+    if (!s) return SCIPNP_OK;
+    for (void* p : s->owned) cudaFree(p);
+    delete s;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_create(const scipnp_params* pp, scipnp_solver** out) {
+    SCIPNP_REQUIRE(pp && out, "null pointer");
+    const scipnp_params& p = *pp;
+    SCIPNP_REQUIRE(p.B >= 1 && p.H >= 1 && p.W >= 1 && p.C >= 1 && p.B <= 65535, "bad dimensions");
+    SCIPNP_REQUIRE(p.method == 0 || p.method == 1, "method must be 0 (GAP) or 1 (ADMM)");
+    SCIPNP_REQUIRE(p.tv_weight > 0.0, "tv_weight must be positive");
+    SCIPNP_REQUIRE(p.tv_iter_max >= 1, "tv_iter_max must be >= 1");
+    if (scipnp_device_count() < 1) {
+        set_error("no CUDA device: libscipnp has no CPU fallback");
+        return SCIPNP_ECUDA;
+    }
+    scipnp_solver* s = new (std::nothrow) scipnp_solver();
+    if (!s) { set_error("out of host memory"); return SCIPNP_ENOMEM; }
+    s->p = p;
+    s->n_meas = (size_t)p.B * p.H * p.W;
+    s->n_frame = s->n_meas * p.C;
+    s->n_phisum = p.phi_batched ? s->n_meas : (size_t)p.H * p.W;
+    s->n_phi = s->n_phisum * p.C;
+    const int mode = p.method == 1 ? MODE_ADMM : (p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN);
+    s->use_fused = p.fused && fused_supported(mode, p.B, p.H, p.W, p.C, p.tv_iter_max);
+    DM(s->xa, s->n_frame, float);
+    DM(s->xb, s->n_frame, float);
+    DM(s->y, s->n_meas, float);
+    DM(s->Phi, s->n_phi, float);
+    DM(s->PhiSum, s->n_phisum, float);
+    DM(s->Xorig, s->n_frame, float);
+    DM(s->sqerr, kPsnrCap, double);
+    DM(s->flags, 4, int);
+    if (p.method == 0) {
+        DM(s->y1a, s->n_meas, float);
+        if (s->use_fused) DM(s->y1b, s->n_meas, float);
+    } else {
+        DM(s->ba, s->n_frame, float);
+        DM(s->xproj, s->n_frame, float);
+        if (s->use_fused) DM(s->bb, s->n_frame, float);
+        else DM(s->fbuf, s->n_frame, float);
+    }
+    if (s->use_fused) {
+        DM(s->xsnap, s->n_frame, float);
+        if (p.method == 0) DM(s->y1snap, s->n_meas, float);
+        else DM(s->bsnap, s->n_frame, float);
+        s->fws_bytes = fused_workspace_bytes(p.B, p.H, p.W, p.C, p.tv_iter_max);
+        DM(s->fws, s->fws_bytes, char);
+    }
+    // exact-path workspace is allocated lazily (only the exact path or a rollback needs it)
+    s->launches0 = g_launches;
+    *out = s;
+    return SCIPNP_OK;
+}
+
+static int ensure_exact_buffers(scipnp_solver* s) {
+    const scipnp_params& p = s->p;
+    if (!s->tvws) {
+        s->tvws_bytes = tv_workspace_bytes(p.B, p.H, p.W, p.C);
+        if (int e = dmalloc(s, &s->tvws, s->tvws_bytes)) return e;
+    }
+    if (p.method == 1 && !s->fbuf)
+        if (int e = dmalloc(s, (void**)&s->fbuf, s->n_frame * sizeof(float))) return e;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_load(scipnp_solver* s, const float* y, const float* Phi, const float* Phi_sum,
+                       const float* x0, const float* X_orig, void* stream) {
+    SCIPNP_REQUIRE(s && y && Phi, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const scipnp_params& p = s->p;
+    SCIPNP_CUDA(cudaMemcpyAsync(s->y, y, s->n_meas * sizeof(float), cudaMemcpyDefault, st));
+    SCIPNP_CUDA(cudaMemcpyAsync(s->Phi, Phi, s->n_phi * sizeof(float), cudaMemcpyDefault, st));
+    if (Phi_sum) {
+        SCIPNP_CUDA(cudaMemcpyAsync(s->PhiSum, Phi_sum, s->n_phisum * sizeof(float), cudaMemcpyDefault, st));
+    } else {
+        if (int e = scipnp_phi_sum(s->Phi, s->PhiSum, p.phi_batched ? p.B : 1, p.H, p.W, p.C, stream)) return e;
+    }
+    if (x0) {
+        SCIPNP_CUDA(cudaMemcpyAsync(s->xa, x0, s->n_frame * sizeof(float), cudaMemcpyDefault, st));
+    } else {
+        if (int e = scipnp_At(s->y, s->Phi, s->xa, p.B, p.H, p.W, p.C, p.phi_batched, stream)) return e;
+    }
+    s->has_orig = X_orig != nullptr;
+    if (X_orig) SCIPNP_CUDA(cudaMemcpyAsync(s->Xorig, X_orig, s->n_frame * sizeof(float), cudaMemcpyDefault, st));
+    if (p.method == 0) {
+        SCIPNP_CUDA(cudaMemsetAsync(s->y1a, 0, s->n_meas * sizeof(float), st));
+    } else {
+        SCIPNP_CUDA(cudaMemsetAsync(s->ba, 0, s->n_frame * sizeof(float), st));
+        // x = x0 until the first projection (pnp_sci_algo.py:800)
+        SCIPNP_CUDA(cudaMemcpyAsync(s->xproj, s->xa, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    SCIPNP_CUDA(cudaMemsetAsync(s->sqerr, 0, kPsnrCap * sizeof(double), st));
+    s->loaded = true;
+    s->iters_done = 0;
+    s->psnr_count = 0;
+    s->refined = 0;
+    return SCIPNP_OK;
+}
+
+// sum of squared errors of iteration k against X_orig, one per batch element
+static int record_sqerr(scipnp_solver* s, int k, const float* x, cudaStream_t st) {
+    if (!s->has_orig || (size_t)(k + 1) * s->p.B > (size_t)kPsnrCap) return SCIPNP_OK;
+    return launch_sq_err(s->Xorig, x, s->n_frame / s->p.B, s->p.B, s->sqerr + (size_t)k * s->p.B, st);
+}
+
+// one outer iteration on the exact path
+static int step_exact(scipnp_solver* s, int k, cudaStream_t st) {
+    const scipnp_params& p = s->p;
+    if (p.method == 0) {
+        int mode = p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN;
+        if (int e = launch_project(mode, s->xa, nullptr, s->xa, nullptr, s->y1a, s->y1a, s->y, s->Phi,
+                                   s->PhiSum, p.lambda, 0.f, p.B, p.H, p.W, p.C, p.phi_batched, st)) return e;
+        if (int e = tv_chambolle_exact(s->xa, s->xb, p.tv_weight, p.tv_eps, p.tv_iter_max, p.B, p.H, p.W,
+                                       p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st)) return e;
+        std::swap(s->xa, s->xb);
+        if (int e = record_sqerr(s, k, s->xa, st)) return e;
+    } else {
+        if (int e = launch_project(MODE_ADMM, s->xa, s->ba, s->xproj, s->fbuf, nullptr, nullptr, s->y,
+                                   s->Phi, s->PhiSum, p.lambda, p.gamma, p.B, p.H, p.W, p.C,
+                                   p.phi_batched, st)) return e;
+        if (int e = tv_chambolle_exact(s->fbuf, s->xa, p.tv_weight, p.tv_eps, p.tv_iter_max, p.B, p.H,
+                                       p.W, p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st)) return e;
+        if (int e = scipnp_admm_dual_update(s->ba, s->xproj, s->xa, s->n_frame, st)) return e;
+        if (int e = record_sqerr(s, k, s->xproj, st)) return e;
+    }
+    return SCIPNP_OK;
+}
+
+static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
+    const scipnp_params& p = s->p;
+    FusedArgs a{};
+    a.x_in = s->xa; a.x_out = s->xb;
+    a.y = s->y; a.Phi = s->Phi; a.Phi_sum = s->PhiSum;
+    a.lambda = p.lambda; a.gamma = p.gamma;
+    a.tv_weight = p.tv_weight; a.tv_eps = p.tv_eps; a.tv_iter_max = p.tv_iter_max;
+    a.B = p.B; a.H = p.H; a.W = p.W; a.C = p.C; a.phi_batched = p.phi_batched;
+    a.workspace = s->fws; a.workspace_bytes = s->fws_bytes;
+    a.flag = s->flags;
+    if (p.method == 0) {
+        a.mode = p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN;
+        a.y1_in = s->y1a; a.y1_out = s->y1b;
+    } else {
+        a.mode = MODE_ADMM;
+        a.b_in = s->ba; a.b_out = s->bb; a.xproj_out = s->xproj;
+    }
+    if (int e = launch_fused(a, st)) return e;
+    std::swap(s->xa, s->xb);
+    if (p.method == 0) { if (p.accelerate) std::swap(s->y1a, s->y1b); }
+    else std::swap(s->ba, s->bb);
+    return record_sqerr(s, k, p.method == 0 ? s->xa : s->xproj, st);
+}
+
+int scipnp_solver_run(scipnp_solver* s, int iters, void* stream) {
+    SCIPNP_REQUIRE(s, "null solver");
+    SCIPNP_REQUIRE(iters >= 0, "negative iteration count");
+    if (!s->loaded) { set_error("scipnp_solver_run before scipnp_solver_load"); return SCIPNP_ESTATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const scipnp_params& p = s->p;
+    const int k0 = s->iters_done;
+    if (!s->use_fused) {
+        if (int e = ensure_exact_buffers(s)) return e;
+        for (int i = 0; i < iters; ++i)
+            if (int e = step_exact(s, k0 + i, st)) return e;
+        s->iters_done += iters;
+        if (s->has_orig) s->psnr_count = s->iters_done < kPsnrCap / p.B ? s->iters_done : kPsnrCap / p.B;
+        return SCIPNP_OK;
+    }
+    // fused path with rollback
+    SCIPNP_CUDA(cudaMemcpyAsync(s->xsnap, s->xa, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1snap, s->y1a, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else SCIPNP_CUDA(cudaMemcpyAsync(s->bsnap, s->ba, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SCIPNP_CUDA(cudaMemsetAsync(s->flags, 0, 4 * sizeof(int), st));
+    for (int i = 0; i < iters; ++i)
+        if (int e = step_fused(s, k0 + i, st)) return e;
+    int flag = 0;
+    SCIPNP_CUDA(cudaMemcpyAsync(&flag, s->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCIPNP_CUDA(cudaStreamSynchronize(st));
+    if (flag) {
+        // the reference would have stopped a TV slice early somewhere in this run:
+        // redo the run on the exact path from the snapshot
+        if (int e = ensure_exact_buffers(s)) return e;
+        SCIPNP_CUDA(cudaMemcpyAsync(s->xa, s->xsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1a, s->y1snap, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        else SCIPNP_CUDA(cudaMemcpyAsync(s->ba, s->bsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        int capi = kPsnrCap / p.B;
+        int n = iters < capi - k0 ? iters : (capi - k0 > 0 ? capi - k0 : 0);
+        if (n > 0) SCIPNP_CUDA(cudaMemsetAsync(s->sqerr + (size_t)k0 * p.B, 0, (size_t)n * p.B * sizeof(double), st));
+        for (int i = 0; i < iters; ++i)
+            if (int e = step_exact(s, k0 + i, st)) return e;
+        s->refined += iters;
+    }
+    s->iters_done += iters;
+    if (s->has_orig) s->psnr_count = s->iters_done < kPsnrCap / p.B ? s->iters_done : kPsnrCap / p.B;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_get_x(scipnp_solver* s, float* x_out, void* stream) {
+    SCIPNP_REQUIRE(s && x_out, "null pointer");
+    if (!s->loaded) { set_error("solver has no inputs"); return SCIPNP_ESTATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* src = s->p.method == 0 ? s->xa : s->xproj;
+    SCIPNP_CUDA(cudaMemcpyAsync(x_out, src, s->n_frame * sizeof(float), cudaMemcpyDefault, st));
+    SCIPNP_CUDA(cudaStreamSynchronize(st));
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_sqerr(scipnp_solver* s, double* sums, int cap, int* count, void* stream) {
+    SCIPNP_REQUIRE(s && count, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int total = s->psnr_count * s->p.B;
+    *count = total;
+    int n = total < cap ? total : cap;
+    if (n <= 0 || !sums) return SCIPNP_OK;
+    SCIPNP_CUDA(cudaMemcpyAsync(sums, s->sqerr, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SCIPNP_CUDA(cudaStreamSynchronize(st));
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_psnr(scipnp_solver* s, double* psnr_all, int cap, int* count, void* stream) {
+    if (int e = scipnp_solver_sqerr(s, psnr_all, cap, count, stream)) return e;
+    int n = *count < cap ? *count : cap;
+    if (!psnr_all) return SCIPNP_OK;
+    const double per = (double)(s->n_frame / s->p.B);
+    for (int i = 0; i < n; ++i) {
+        double mse = psnr_all[i] / per;
+        psnr_all[i] = (mse == 0.0) ? 100.0 : 20.0 * log10(1.0 / sqrt(mse));   // utils.py:32-36
+    }
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_refined_iters(scipnp_solver* s, int* count) {
+    SCIPNP_REQUIRE(s && count, "null pointer");
+    *count = s->refined;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_state(scipnp_solver* s, float** x_cur, float** y1_cur) {
+    SCIPNP_REQUIRE(s, "null solver");
+    if (x_cur) *x_cur = s->xa;
+    if (y1_cur) *y1_cur = s->p.method == 0 ? s->y1a : s->ba;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_uses_fused(scipnp_solver* s) { return s && s->use_fused ? 1 : 0; }
+
+long long scipnp_solver_launch_count(scipnp_solver* s) { return s ? g_launches - s->launches0 : 0; }
+
+static int denoise_host(int method, const float* y, const float* Phi, const float* x0,
+                        const float* X_orig, const scipnp_params* p, int iters, float* x_out,
+                        double* psnr_all, int* psnr_count) {
+    SCIPNP_REQUIRE(p && y && Phi && x_out, "null pointer");
+    scipnp_params q = *p;
+    q.method = method;
+    scipnp_solver* s = nullptr;
+    if (int e = scipnp_solver_create(&q, &s)) return e;
+    int e = scipnp_solver_load(s, y, Phi, nullptr, x0, X_orig, nullptr);
+    if (!e) e = scipnp_solver_run(s, iters, nullptr);
+    if (!e) e = scipnp_solver_get_x(s, x_out, nullptr);
+    int cnt = 0;
+    if (!e) e = scipnp_solver_psnr(s, psnr_all, psnr_all ? iters * q.B : 0, &cnt, nullptr);
+    if (psnr_count) *psnr_count = cnt;
+    scipnp_solver_destroy(s);
+    return e;
+}
+
+int scipnp_gap_denoise_host(const float* y, const float* Phi, const float* x0, const float* X_orig,
+                            const scipnp_params* p, int iters, float* x_out, double* psnr_all,
+                            int* psnr_count) {
+    return denoise_host(0, y, Phi, x0, X_orig, p, iters, x_out, psnr_all, psnr_count);
+}
+
+int scipnp_admm_denoise_host(const float* y, const float* Phi, const float* x0, const float* X_orig,
+                             const scipnp_params* p, int iters, float* x_out, double* psnr_all,
+                             int* psnr_count) {
+    return denoise_host(1, y, Phi, x0, X_orig, p, iters, x_out, psnr_all, psnr_count);
+}
+
+}  // extern "C"

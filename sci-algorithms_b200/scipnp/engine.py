@@ -1,0 +1,175 @@
+"""Host-side plumbing over the C ABI: device buffers, streams, the solver handle.
+
+PyTorch is used only for device memory, pinned host memory and streams.  Every
+function here ends in a call into libscipnp.so; nothing computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, Params, require_device, ScipnpError
+
+__all__ = ["Solver", "to_device", "stream_ptr", "is_torch", "dptr", "f32c"]
+
+METHOD_GAP, METHOD_ADMM = 0, 1
+
+
+def is_torch(a):
+    return isinstance(a, torch.Tensor)
+
+
+def f32c(a):
+    """float32, C-contiguous NumPy view/copy of an array-like (the engine
+    computes in single precision; float64 inputs of the pnp_sci_test_* drivers
+    are narrowed here, once)."""
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def to_device(a, device=None):
+    """array-like / tensor -> contiguous float32 CUDA tensor."""
+    require_device()
+    if is_torch(a):
+        t = a
+        if not t.is_cuda:
+            t = t.to(device or "cuda", non_blocking=True)
+        return t.contiguous().to(torch.float32)
+    return torch.from_numpy(f32c(a)).to(device or "cuda")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dptr(t):
+    """Raw pointer of a tensor / ndarray (or None)."""
+    if t is None:
+        return None
+    if is_torch(t):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+class Solver:
+    """Persistent GAP-TV / ADMM-TV solver (``scipnp_solver_*``).
+
+    All arrays are [B,H,W,C] / [B,H,W] float32; ``Phi`` is [H,W,C] (shared) or
+    [B,H,W,C] (``phi_batched``).  Inputs may be NumPy arrays (copied H2D by the
+    library) or CUDA tensors (copied D2D).
+    """
+
+    def __init__(self, B, H, W, C, method="gap", accelerate=True, _lambda=1.0, gamma=0.01,
+                 tv_weight=0.1, tv_iter_max=5, tv_eps=2.e-4, phi_batched=False, fused=True):
+        require_device()
+        self.shape = (int(B), int(H), int(W), int(C))
+        self.method = METHOD_ADMM if str(method).lower() == "admm" else METHOD_GAP
+        p = Params()
+        p.method = self.method
+        p.accelerate = 1 if accelerate else 0
+        p.lambda_ = float(_lambda)
+        p.gamma = float(gamma)
+        p.tv_weight = float(tv_weight)
+        p.tv_eps = float(tv_eps)
+        p.tv_iter_max = int(tv_iter_max)
+        p.fused = 1 if fused else 0
+        p.B, p.H, p.W, p.C = self.shape
+        p.phi_batched = 1 if phi_batched else 0
+        p.halo_rows = 0
+        self.params = p
+        h = C.c_void_p()
+        check(lib.scipnp_solver_create(C.byref(p), C.byref(h)))
+        self._h = h
+        self._keep = []
+
+    # -- lifecycle ----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.scipnp_solver_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- data -----------------------------------------------------------------
+    def _chk(self, a, shape, name):
+        if a is None:
+            return None
+        if not is_torch(a):
+            a = f32c(a)
+        elif a.dtype != torch.float32 or not a.is_contiguous():
+            a = a.contiguous().to(torch.float32)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError("%s has shape %s, expected %s" % (name, tuple(a.shape), tuple(shape)))
+        self._keep.append(a)
+        return a
+
+    def load(self, y, Phi, Phi_sum=None, x0=None, X_orig=None):
+        B, H, W, Cc = self.shape
+        pb = self.params.phi_batched
+        self._keep = []
+        y = self._chk(y, (B, H, W), "y")
+        Phi = self._chk(Phi, (B, H, W, Cc) if pb else (H, W, Cc), "Phi")
+        Phi_sum = self._chk(Phi_sum, (B, H, W) if pb else (H, W), "Phi_sum")
+        x0 = self._chk(x0, (B, H, W, Cc), "x0")
+        X_orig = self._chk(X_orig, (B, H, W, Cc), "X_orig")
+        check(lib.scipnp_solver_load(self._h, dptr(y), dptr(Phi), dptr(Phi_sum), dptr(x0),
+                                     dptr(X_orig), stream_ptr()))
+        if any(not is_torch(a) for a in self._keep):
+            torch.cuda.current_stream().synchronize()   # pageable host sources
+        self._keep = []
+
+    def run(self, iters):
+        check(lib.scipnp_solver_run(self._h, int(iters), stream_ptr()))
+
+    def get_x(self, out=None):
+        """Current estimate as NumPy (default) or into a given tensor/array."""
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float32)
+        check(lib.scipnp_solver_get_x(self._h, dptr(out), stream_ptr()))
+        return out
+
+    def _per_iter(self, fn):
+        n = C.c_int(0)
+        check(fn(self._h, None, 0, C.byref(n), stream_ptr()))
+        B = self.shape[0]
+        if n.value == 0:
+            return np.zeros((0, B))
+        buf = (C.c_double * n.value)()
+        check(fn(self._h, buf, n.value, C.byref(n), stream_ptr()))
+        return np.array(buf[:n.value], dtype=np.float64).reshape(-1, B)
+
+    def psnr_all(self):
+        """utils.psnr per (iteration, batch element): array [iters, B]."""
+        return self._per_iter(lib.scipnp_solver_psnr)
+
+    def sqerr_all(self):
+        """sum (x - X_orig)^2 per (iteration, batch element): array [iters, B]."""
+        return self._per_iter(lib.scipnp_solver_sqerr)
+
+    @property
+    def refined_iters(self):
+        n = C.c_int(0)
+        check(lib.scipnp_solver_refined_iters(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def uses_fused(self):
+        return bool(lib.scipnp_solver_uses_fused(self._h))
+
+    @property
+    def launches(self):
+        return int(lib.scipnp_solver_launch_count(self._h))
+
+    def state_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        check(lib.scipnp_solver_state(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value

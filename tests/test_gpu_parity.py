@@ -1,0 +1,361 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed golden
+fixtures of the reference and against the CPU oracle on fresh seeded inputs.
+
+Tolerance (BASELINE.json north_star): max abs error <= 1e-4 on [0,1] frames and
+PSNR within 0.01 dB at equal iteration count.  The exact path reproduces the
+reference's float32 arithmetic statement by statement and is held to 2e-6.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_X = 1e-4          # north_star: max abs on [0,1] frames
+TOL_DB = 0.01         # north_star: PSNR delta
+TOL_EXACT = 2e-6      # exact path (IEEE statement-order replica)
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import scipnp
+    from scipnp import _lib
+    assert _lib.lib.scipnp_device_count() >= 1
+    return scipnp
+
+
+@pytest.fixture(params=[True, False], ids=["fused", "exact"])
+def path(request, sp):
+    from scipnp import pnp_sci_algo as M
+    old = M.USE_FUSED
+    M.USE_FUSED = request.param
+    yield request.param
+    M.USE_FUSED = old
+
+
+def _tol(fused):
+    return TOL_X if fused else TOL_EXACT
+
+
+def _ops(mask):
+    from oracle import pnp_sci as O
+    return (lambda x: O.A_(x, mask)), (lambda y: O.At_(y, mask))
+
+
+def _cmp(x, gx, pa, gpa, fused):
+    err = float(np.abs(x - gx).max())
+    assert err <= _tol(fused), "max abs %.3g" % err
+    if gpa is not None and len(gpa):
+        assert len(pa) == len(gpa)
+        assert np.abs(np.array(pa) - np.array(gpa)).max() <= TOL_DB
+
+
+# -- operators -----------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["ops_8", "ops_5"])
+def test_operators_bit_exact(sp, golden, tag):
+    g = golden(tag)
+    np.testing.assert_array_equal(sp.A_(g["x"], g["Phi"]), g["A"])
+    np.testing.assert_array_equal(sp.At_(g["y"], g["Phi"]), g["At"])
+    np.testing.assert_array_equal(sp.phi_sum(g["Phi"]), g["Phi_sum"])
+    assert abs(sp.psnr(g["x"], g["x2"]) - float(g["psnr"])) < 1e-4
+    assert sp.psnr(g["x"], g["x"]) == 100
+
+
+def test_operator_properties_large(sp):
+    """Size-independent properties at the UHD size of config 5."""
+    import torch
+    H, W, Cc = 2160, 3840, 24
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    Phi = (torch.rand((H, W, Cc), device="cuda", generator=gen) <= 0.5).float()
+    x = torch.rand((H, W, Cc), device="cuda", generator=gen)
+    y = torch.rand((H, W), device="cuda", generator=gen)
+    Ax = sp.A_(x, Phi)
+    Aty = sp.At_(y, Phi)
+    # adjoint identity <A x, y> = <x, At y>
+    lhs = float((Ax.double() * y.double()).sum())
+    rhs = float((x.double() * Aty.double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * abs(lhs)
+    # A(At(y)/Phi_sum) = y wherever some mask is open (binary mask: A At = diag(Phi_sum))
+    ps = sp.phi_sum(Phi)
+    back = sp.A_(sp.At_(y / ps, Phi), Phi)
+    open_ = Phi.sum(2) > 0
+    assert float((back - y)[open_].abs().max()) <= 2e-6
+    assert float(ps.min()) >= 1.0
+
+
+# -- TV --------------------------------------------------------------------------
+
+@pytest.mark.parametrize("T", [1, 2, 5, 200])
+def test_tv_regression_vectors(sp, golden, T):
+    g = golden("tv_T%d" % T)
+    out, n_exec, energy = sp.denoise_tv_chambolle(g["image"], float(g["weight"]),
+                                                  n_iter_max=int(g["n_iter_max"]),
+                                                  multichannel=True, return_stats=True)
+    np.testing.assert_array_equal(n_exec, g["n_exec"])      # same early-stop decisions
+    assert np.abs(out - g["out"]).max() <= TOL_EXACT
+    ne = int(g["n_exec"].max())
+    np.testing.assert_allclose(energy[:, :ne], g["energy"][:, :ne], rtol=1e-5)
+
+
+def test_tv_single_channel_2d(sp):
+    from oracle.tv_chambolle import denoise_tv_chambolle as otv
+    rng = np.random.default_rng(11)
+    f = rng.random((33, 47)).astype(np.float32)
+    out = sp.denoise_tv_chambolle(f, 0.2, n_iter_max=7)
+    assert np.abs(out - otv(f, 0.2, n_iter_max=7)).max() <= TOL_EXACT
+
+
+def test_tv_properties_large(sp):
+    import torch
+    H, W, Cc = 1080, 1920, 24
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    f = torch.rand((H, W, Cc), device="cuda", generator=gen)
+    out = sp.denoise_tv_chambolle(f, 0.3, n_iter_max=5, multichannel=True)
+    # f + div p keeps the mean of every channel
+    assert float((out.double().mean((0, 1)) - f.double().mean((0, 1))).abs().max()) < 1e-6
+    # constant image is a fixed point
+    c = torch.full((64, 64, 8), 0.25, device="cuda")
+    assert torch.equal(sp.denoise_tv_chambolle(c, 0.3, n_iter_max=5, multichannel=True), c)
+    # channels are independent problems
+    one = sp.denoise_tv_chambolle(f[:, :, 3].contiguous(), 0.3, n_iter_max=5)
+    assert torch.equal(one, out[:, :, 3])
+    # total variation does not increase
+    def tv(u):
+        return float((u[1:] - u[:-1]).abs().sum() + (u[:, 1:] - u[:, :-1]).abs().sum())
+    assert tv(out) < tv(f)
+
+
+# -- solver loops against the reference's golden outputs ---------------------------
+
+def test_gap_accelerated_golden(sp, golden, path):
+    g = golden("gap_acc")
+    A, At = _ops(g["mask"])
+    x, ps, ss, pa = sp.gap_denoise(g["y"], g["mask"].sum(2), A, At, _lambda=1, accelerate=True,
+                                   denoiser='tv', iter_max=12, tv_weight=0.3, tv_iter_max=5,
+                                   X_orig=g["X_orig"])
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+    assert x.dtype == np.float32
+    assert np.abs(np.array(ps) - g["psnr"]).max() <= TOL_DB
+    assert np.abs(np.array(ss) - g["ssim"]).max() <= 1e-4
+
+
+def test_gap_plain_schedule_golden(sp, golden, path):
+    g = golden("gap_plain")
+    x, _, _, pa = sp.gap_denoise(g["y"], g["mask"].sum(2), Phi=g["mask"], _lambda=0.75,
+                                 accelerate=False, denoiser='tv', iter_max=[3, 4],
+                                 sigma=[0.2, 0.1], tv_weight=0.1, tv_iter_max=3,
+                                 X_orig=g["X_orig"])
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+
+
+def test_admm_golden(sp, golden, path):
+    g = golden("admm")
+    A, At = _ops(g["mask"])
+    x, ps, ss, pa = sp.admm_denoise(g["y"], g["mask"].sum(2), A, At, _lambda=1, gamma=0.01,
+                                    denoiser='tv', iter_max=12, tv_weight=0.3, tv_iter_max=5,
+                                    X_orig=g["X_orig"])
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+    assert np.abs(np.array(ps) - g["psnr"]).max() <= TOL_DB
+
+
+def test_gap_warm_start_ragged_golden(sp, golden, path):
+    g = golden("gap_c5_warm")        # C = 5: the scalar (non-vectorised) kernels
+    ms = g["mask"].sum(2)
+    ms[ms == 0] = 1
+    x, _, _, pa = sp.gap_denoise(g["y"], ms, Phi=g["mask"], iter_max=6, tv_weight=0.2,
+                                 tv_iter_max=4, x0=g["x0"], X_orig=g["X_orig"])
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+
+
+@pytest.mark.parametrize("pm", ["gap", "admm"])
+@pytest.mark.parametrize("md", ["plain", "updown"])
+def test_cacti_wrapper_golden(sp, golden, path, pm, md):
+    g = golden("cacti_%s_%s" % (pm, md))
+    A, At = _ops(g["mask"])
+    kw = dict(_lambda=1, denoiser='tv', iter_max=5, tv_weight=0.3, tv_iter_max=5)
+    kw.update({"accelerate": True} if pm == "gap" else {"gamma": 0.01})
+    x_, t_, ps, ss, pa = sp.admmdenoise_cacti(g["meas"], g["mask"], A, At, projmeth=pm,
+                                              orig=g["orig"], nframe=2, MAXB=255.,
+                                              maskdirection=md, **kw)
+    assert x_.shape == g["x"].shape and x_.dtype == np.float32
+    assert np.abs(x_ - g["x"]).max() <= _tol(path)
+    assert np.abs(np.array(pa) - g["psnr_all"]).max() <= TOL_DB
+    assert np.abs(np.array(ps) - g["psnr"]).max() <= TOL_DB
+    assert t_ > 0
+
+
+def test_cacti_wrapper_without_orig(sp, golden):
+    g = golden("cacti_gap_plain")
+    x_, t_, ps, ss, pa = sp.admmdenoise_cacti(g["meas"], g["mask"], None, None, projmeth='gap',
+                                              nframe=2, MAXB=255., denoiser='tv', iter_max=5,
+                                              tv_weight=0.3, tv_iter_max=5)
+    assert np.abs(x_ - g["x"]).max() <= TOL_X
+    assert ps == [] and ss == [] and pa == [[], []]
+
+
+def test_bayer_golden(sp, golden, path):
+    g = golden("bayer")
+    x, ps, ss, pa = sp.gap_denoise_bayer(g["y_bayer"], g["Phi_bayer"], _lambda=1, accelerate=True,
+                                         denoiser='tv', iter_max=8, tv_weight=0.1, tv_iter_max=5,
+                                         X_orig=g["X_orig"])
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+    assert np.abs(np.array(ps) - g["psnr"]).max() <= TOL_DB
+
+
+def test_cassi_golden(sp, golden, path):
+    g = golden("cassi")
+    x, _, _, pa = sp.gap_denoise_cassi(g["y"], g["mask2d"], int(g["nband"]), int(g["step"]),
+                                       iter_max=8, tv_weight=0.1, tv_iter_max=5,
+                                       X_orig=g["X_orig"])
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+
+
+# -- fresh inputs against the oracle at the reference's demo configuration -----------
+
+def test_config1_gap_tv_40_iterations(sp, path):
+    """BASELINE config 1 (256x256x8, 40 it, tv_weight 0.3, tv_iter_max 5)."""
+    from oracle import pnp_sci as O
+    from scipnp import synth
+    meas, mask, orig = synth.make_cacti(256, 256, 8, 1, cfg=1)
+    A, At = _ops(mask)
+    kw = dict(projmeth='gap', orig=orig, nframe=1, MAXB=255., _lambda=1, accelerate=True,
+              denoiser='tv', iter_max=40, tv_weight=0.3, tv_iter_max=5)
+    xo, _, pso, sso, pao = O.admmdenoise_cacti(meas, mask, A, At, **kw)
+    xg, _, psg, ssg, pag = sp.admmdenoise_cacti(meas, mask, A, At, **kw)
+    assert np.abs(xg - xo).max() <= _tol(path)
+    assert np.abs(np.array(pag) - np.array(pao)).max() <= TOL_DB
+    assert np.abs(np.array(psg) - np.array(pso)).max() <= TOL_DB
+    assert np.abs(np.array(ssg) - np.array(sso)).max() <= 1e-4
+    assert pag[0][-1] > 24.0          # the reconstruction actually converges
+
+
+def test_config2_admm_batch(sp, path):
+    """BASELINE config 2 shape: several 256x256x8 measurements solved as one batch."""
+    from oracle import pnp_sci as O
+    from scipnp import synth
+    meas, mask, orig = synth.make_cacti(256, 256, 8, 3, cfg=2)
+    A, At = _ops(mask)
+    kw = dict(projmeth='admm', orig=orig, nframe=3, MAXB=255., _lambda=1, gamma=0.01,
+              denoiser='tv', iter_max=10, tv_weight=0.3, tv_iter_max=5)
+    xo, _, pso, _, pao = O.admmdenoise_cacti(meas, mask, A, At, **kw)
+    xg, _, psg, _, pag = sp.admmdenoise_cacti(meas, mask, A, At, **kw)
+    assert np.abs(xg - xo).max() <= _tol(path)
+    assert np.abs(np.array(pag) - np.array(pao)).max() <= TOL_DB
+
+
+def test_uhd_crop_matches_oracle(sp, path):
+    """A 96-row, full-width (3840) crop of the config-5 scene, 3 iterations."""
+    from oracle import pnp_sci as O
+    from scipnp import synth
+    meas, mask, orig = synth.make_cacti(96, 3840, 24, 1, cfg=5)
+    A, At = _ops(mask)
+    y = meas[:, :, 0] / np.float32(255.)
+    ms = O.phi_sum(mask)
+    xo, _, _, pao = O.gap_denoise(y, ms, A, At, iter_max=3, tv_weight=0.3, tv_iter_max=5,
+                                  X_orig=orig / np.float32(255.))
+    xg, _, _, pag = sp.gap_denoise(y, ms, Phi=mask, iter_max=3, tv_weight=0.3, tv_iter_max=5,
+                                   X_orig=orig / np.float32(255.))
+    assert np.abs(xg - xo).max() <= _tol(path)
+    assert np.abs(np.array(pag) - np.array(pao)).max() <= TOL_DB
+
+
+def test_uhd_full_size_properties(sp):
+    """Config 5 at full size (3840x2160x24): properties the domain offers, since
+    the oracle needs ~40 s per iteration there."""
+    import torch
+    from scipnp import Solver
+    H, W, Cc = 2160, 3840, 24
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    Phi = (torch.rand((H, W, Cc), device="cuda", generator=gen) <= 0.5).float()
+    yy = torch.arange(H, device="cuda").float()[:, None, None]
+    xx = torch.arange(W, device="cuda").float()[None, :, None]
+    tt = torch.arange(Cc, device="cuda").float()[None, None, :]
+    orig = 0.5 + 0.3 * torch.sin((xx + 3 * tt) / 97.) * torch.cos(yy / 131.)
+    y = (Phi * orig).sum(2)
+    with Solver(1, H, W, Cc, method="gap", tv_weight=0.3, tv_iter_max=5) as s:
+        s.load(y[None], Phi, X_orig=orig[None])
+        s.run(6)
+        pa = s.psnr_all()[:, 0]
+        x_full = torch.empty((1, H, W, Cc), device="cuda")
+        s.get_x(x_full)
+        fused = s.uses_fused
+    assert np.all(np.diff(pa) > 0) and pa[-1] > 20.0     # PSNR climbs monotonically
+    # a horizontal band solved alone agrees with the full solve away from the cut:
+    # information travels <= (tv_iter_max-1) rows per outer iteration
+    r0, r1, it = 1000, 1128, 6
+    with Solver(1, r1 - r0, W, Cc, method="gap", tv_weight=0.3, tv_iter_max=5) as s:
+        s.load(y[None, r0:r1].contiguous(), Phi[r0:r1].contiguous())
+        s.run(it)
+        x_band = torch.empty((1, r1 - r0, W, Cc), device="cuda")
+        s.get_x(x_band)
+    m = 4 * it
+    d = (x_band[0, m:-m] - x_full[0, r0 + m:r1 - m]).abs().max()
+    assert float(d) <= (1e-5 if fused else 0.0)
+
+
+# -- the C ABI called directly ----------------------------------------------------------
+
+def test_c_abi_host_entry_matches_python_surface(sp, golden):
+    from scipnp._lib import lib, Params, check
+    g = golden("gap_acc")
+    H, W, Cc = g["mask"].shape
+    p = Params()
+    p.method, p.accelerate, p.lambda_, p.gamma = 0, 1, 1.0, 0.0
+    p.tv_weight, p.tv_eps, p.tv_iter_max, p.fused = 0.3, 2e-4, 5, 0
+    p.B, p.H, p.W, p.C, p.phi_batched, p.halo_rows = 1, H, W, Cc, 0, 0
+    y = np.ascontiguousarray(g["y"], np.float32)
+    Phi = np.ascontiguousarray(g["mask"], np.float32)
+    Xo = np.ascontiguousarray(g["X_orig"], np.float32)
+    x = np.empty((H, W, Cc), np.float32)
+    pa = (C.c_double * 12)()
+    n = C.c_int(0)
+    check(lib.scipnp_gap_denoise_host(y.ctypes.data, Phi.ctypes.data, None, Xo.ctypes.data,
+                                      C.byref(p), 12, x.ctypes.data, pa, C.byref(n)))
+    assert n.value == 12
+    assert np.abs(x - g["x"]).max() <= TOL_EXACT
+    assert np.abs(np.array(pa[:]) - g["psnr_all"]).max() <= TOL_DB
+    # ADMM through the same door
+    g = golden("admm")
+    p.gamma = 0.01
+    check(lib.scipnp_admm_denoise_host(y.ctypes.data, Phi.ctypes.data, None, Xo.ctypes.data,
+                                       C.byref(p), 12, x.ctypes.data, pa, C.byref(n)))
+    assert np.abs(x - g["x"]).max() <= TOL_EXACT
+    assert lib.scipnp_launch_count() > 0
+
+
+def test_c_abi_rejects_bad_arguments(sp):
+    from scipnp._lib import lib
+    assert lib.scipnp_A(None, None, None, 1, 4, 4, 4, 0, None) == -1
+    assert b"null" in lib.scipnp_last_error()
+    assert lib.scipnp_tv_chambolle(None, None, 0.1, 2e-4, 5, 1, 0, 4, 4, None, 0, None, None, 0, None) == -1
+
+
+def test_early_stop_rolls_back_to_exact_path(sp):
+    """Huge eps forces the energy criterion to fire: the solver must give the
+    reference's (early-stopped) answer whichever path it started on."""
+    from oracle import pnp_sci as O
+    from oracle.tv_chambolle import denoise_tv_chambolle as otv
+    from scipnp import synth, Solver
+    meas, mask, orig = synth.make_cacti(64, 64, 8, 1, cfg=9)
+    y = meas[:, :, 0] / np.float32(255.)
+    ms = O.phi_sum(mask)
+    eps = 0.5
+    # oracle loop with the big eps
+    x = O.At_(y, mask)
+    y1 = np.zeros_like(y)
+    for _ in range(4):
+        yb = O.A_(x, mask)
+        y1 = y1 + (y - yb)
+        x = x + 1 * O.At_((y1 - yb) / ms, mask)
+        x = otv(x, 0.3, eps=eps, n_iter_max=5, multichannel=True)
+    with Solver(1, 64, 64, 8, method="gap", tv_weight=0.3, tv_iter_max=5, tv_eps=eps) as s:
+        s.load(y[None], mask)
+        s.run(4)
+        xg = s.get_x()[0]
+        if s.uses_fused:
+            assert s.refined_iters == 4
+    assert np.abs(xg - x).max() <= TOL_EXACT
