@@ -3,7 +3,7 @@
 PyTorch is used only for device memory, pinned host memory and streams.  Every
 function here ends in a call into libscipnp.so; nothing computes on the CPU.
 """
-import ctypes as C
+import ctypes as ct
 
 import numpy as np
 import torch
@@ -38,7 +38,7 @@ def to_device(a, device=None):
 
 
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ct.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def dptr(t):
@@ -46,8 +46,8 @@ def dptr(t):
     if t is None:
         return None
     if is_torch(t):
-        return C.c_void_p(t.data_ptr())
-    return C.c_void_p(t.ctypes.data)
+        return ct.c_void_p(t.data_ptr())
+    return ct.c_void_p(t.ctypes.data)
 
 
 class Solver:
@@ -76,8 +76,8 @@ class Solver:
         p.phi_batched = 1 if phi_batched else 0
         p.halo_rows = 0
         self.params = p
-        h = C.c_void_p()
-        check(lib.scipnp_solver_create(C.byref(p), C.byref(h)))
+        h = ct.c_void_p()
+        check(lib.scipnp_solver_create(ct.byref(p), ct.byref(h)))
         self._h = h
         self._keep = []
 
@@ -138,13 +138,13 @@ class Solver:
         return out
 
     def _per_iter(self, fn):
-        n = C.c_int(0)
-        check(fn(self._h, None, 0, C.byref(n), stream_ptr()))
+        n = ct.c_int(0)
+        check(fn(self._h, None, 0, ct.byref(n), stream_ptr()))
         B = self.shape[0]
         if n.value == 0:
             return np.zeros((0, B))
-        buf = (C.c_double * n.value)()
-        check(fn(self._h, buf, n.value, C.byref(n), stream_ptr()))
+        buf = (ct.c_double * n.value)()
+        check(fn(self._h, buf, n.value, ct.byref(n), stream_ptr()))
         return np.array(buf[:n.value], dtype=np.float64).reshape(-1, B)
 
     def psnr_all(self):
@@ -157,8 +157,8 @@ class Solver:
 
     @property
     def refined_iters(self):
-        n = C.c_int(0)
-        check(lib.scipnp_solver_refined_iters(self._h, C.byref(n)))
+        n = ct.c_int(0)
+        check(lib.scipnp_solver_refined_iters(self._h, ct.byref(n)))
         return n.value
 
     @property
@@ -170,6 +170,6 @@ class Solver:
         return int(lib.scipnp_solver_launch_count(self._h))
 
     def state_ptrs(self):
-        a, b = C.c_void_p(), C.c_void_p()
-        check(lib.scipnp_solver_state(self._h, C.byref(a), C.byref(b)))
+        a, b = ct.c_void_p(), ct.c_void_p()
+        check(lib.scipnp_solver_state(self._h, ct.byref(a), ct.byref(b)))
         return a.value, b.value
