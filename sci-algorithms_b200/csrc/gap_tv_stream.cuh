@@ -6,8 +6,8 @@
 namespace scipnp {
 namespace fusedk {
 
-
 constexpr int RB = 4;             // rows per staged block
+constexpr int NSLOT = 3;          // staging ring: block b in slot b % 3
 constexpr int PADL = 33;          // padded lane stride of the transposed tiles (float4 units)
 constexpr int kMaxWarps = 8;
 
@@ -34,15 +34,13 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ float fast_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float fast_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 
-struct F4 { float v[4]; };
-__device__ __forceinline__ F4 lds4(const float4* p) { float4 t = *p; F4 r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r; }
-
 // shared-memory carve-up (per CTA), all offsets in bytes
 struct Smem {
     int tile_f4_per_row;     // float4 slots of one of {x, Phi} for one row: NG*K*PADL
     int row_bytes;           // one staged row: 2 tiles + y, y1, Phi_sum lanes
     int buf_bytes;           // RB rows
-    int part_off;            // partial dot products [RB][NG][32][KP]
+    int part_off;            // partial dot products, two buffers of [RB][NG][32][KP]
+    int part_bytes;
     int KP;
     int total;
 };
@@ -52,8 +50,9 @@ __host__ __device__ constexpr Smem smem_layout(int K, int NG) {
     s.row_bytes = 2 * s.tile_f4_per_row * 16 + 3 * NG * 32 * 4;
     s.buf_bytes = RB * s.row_bytes;
     s.KP = (K + 3) & ~3;
-    s.part_off = 2 * s.buf_bytes;
-    s.total = s.part_off + RB * NG * 32 * s.KP * 4;
+    s.part_off = NSLOT * s.buf_bytes;
+    s.part_bytes = RB * NG * 32 * s.KP * 4;
+    s.total = s.part_off + 2 * s.part_bytes;
     return s;
 }
 
@@ -72,45 +71,133 @@ __device__ __forceinline__ P2 shfl_up2(P2 a) {
     return make_float2(__shfl_up_sync(0xffffffffu, a.x, 1), __shfl_up_sync(0xffffffffu, a.y, 1));
 }
 
-// CTA size per chunk count K = C/4: NG = 8/K pixel groups of K chunk-warps each
-__host__ __device__ constexpr int fused_groups(int K) { return 8 / K < 1 ? 1 : 8 / K; }
+// CTA size per chunk count K = C/4: NG = 6/K pixel groups of K chunk-warps each (<= ~90 KB of
+// staging per CTA so that two CTAs share an SM)
+__host__ __device__ constexpr int fused_groups(int K) { return 6 / K < 1 ? 1 : 6 / K; }
 __host__ __device__ constexpr int fused_threads(int K) { return fused_groups(K) * K * 32; }
+
+// Register state of one thread: 4 channels as two packed pairs, R pipeline stages.
+template <int R>
+struct Pipe {
+    P2 o_prev[R][2];      // out_i(rho-i-1)
+    P2 g1_prev[R][2];     // horizontal difference of out_i at row rho-i-1
+    P2 P0[R + 1][2];      // P[i] = p^i(rho-i-1), vertical component; P[0] stays 0
+    P2 P1[R + 1][2];      //                       horizontal component
+    P2 fd[R][2];          // fd[j] = f(rho-1-j)
+    P2 en[R][2];          // energy partials of dual iterations 0..R-1
+};
+
+struct StepConst {
+    P2 mone2, mtau2, tvc2, one2, wm2;   // wm2 = w on owned pixels (fast path)
+    float tvw, own_f, pxin_f;
+    int src_right;
+    int rs, r0, r1, H;
+};
+
+// One pipeline step: f_new = f(rho) enters, out_R(rho-R) is returned in o_new.
+// FAST: every row touched by the R stages lies inside the segment and the image, so no
+// row masks are needed; energy contributions are masked per lane at the very end.
+template <int R, bool CHECK, bool FAST>
+__device__ __forceinline__ void pipe_step(Pipe<R>& S, const StepConst& c, int rho, const P2 (&f_new)[2], P2 (&o_new)[2]) {
+    o_new[0] = f_new[0];
+    o_new[1] = f_new[1];
+    P2 pend0[2], pend1[2];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int row_new = rho - i;          // row of o_new = out_i(row_new)
+        const int u = row_new - 1;            // row whose dual variable advances
+        // general path: masks as multipliers.  The dual variable of a row outside the
+        // segment/image or of a pixel outside the image stays 0; g0 = 0 below the last row.
+        P2 m2, md2, me2, wm2;
+        if (!FAST) {
+            m2 = splat(((u >= c.rs) && (u < c.H)) ? c.pxin_f : 0.f);
+            md2 = splat(row_new < c.H ? 1.f : 0.f);
+            const float me = (u >= c.r0 && u < c.r1) ? 1.f : 0.f;
+            me2 = splat(me);
+            wm2 = splat(me * c.tvw);
+        } else {
+            wm2 = c.wm2;
+        }
+        P2 pi0[2], pi1[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { pi0[q] = S.P0[i][q]; pi1[q] = S.P1[i][q]; }
+        if (i > 0) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { S.P0[i][q] = pend0[q]; S.P1[i][q] = pend1[q]; }
+        }
+        P2 o_next[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const P2 o_right = shfl_idx2(o_new[q], c.src_right);
+            P2 g0 = fma2(S.o_prev[i][q], c.mone2, o_new[q]);
+            if (!FAST) g0 = mul2(g0, md2);
+            const P2 g1 = S.g1_prev[i][q];
+            const P2 nrm = sqrt2(fma2(g0, g0, mul2(g1, g1)));
+            P2 r = rcp2(fma2(nrm, c.tvc2, c.one2));
+            if (!FAST) r = mul2(r, m2);
+            const P2 pn0 = mul2(fma2(g0, c.mtau2, pi0[q]), r);
+            const P2 pn1 = mul2(fma2(g1, c.mtau2, pi1[q]), r);
+            const P2 p1l = shfl_up2(pn1);
+            // D(p^{i+1})(u) = (p0(u-1) - p0(u)) + (p1(u, left) - p1(u))
+            const P2 d = add2(fma2(pn0, c.mone2, S.P0[i + 1][q]), fma2(pn1, c.mone2, p1l));
+            o_next[q] = add2(S.fd[i][q], d);
+            if (CHECK) {
+                S.en[i][q] = fma2(nrm, wm2, S.en[i][q]);                              // w*|grad out_i|(u)
+                if (i + 1 < R) {
+                    if (FAST) S.en[i + 1][q] = fma2(d, d, S.en[i + 1][q]);            // D(p^{i+1})(u)^2
+                    else S.en[i + 1][q] = fma2(mul2(d, me2), d, S.en[i + 1][q]);
+                }
+            }
+            S.g1_prev[i][q] = fma2(o_new[q], c.mone2, o_right);
+            S.o_prev[i][q] = o_new[q];
+            pend0[q] = pn0;
+            pend1[q] = pn1;
+        }
+        o_new[0] = o_next[0];
+        o_new[1] = o_next[1];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { S.P0[R][q] = pend0[q]; S.P1[R][q] = pend1[q]; }
+#pragma unroll
+    for (int i = R - 1; i > 0; --i) { S.fd[i][0] = S.fd[i - 1][0]; S.fd[i][1] = S.fd[i - 1][1]; }
+    S.fd[0][0] = f_new[0];
+    S.fd[0][1] = f_new[1];
+}
 
 template <int R, int MODE, bool CHECK, int K>
 __global__ void __launch_bounds__(fused_threads(K), 2)
 gap_tv_stream_kernel(const FusedParams p) {
     constexpr int NG = fused_groups(K);
     constexpr int NT = fused_threads(K);
+    constexpr Smem L = smem_layout(K, NG);
+    constexpr int OWN = 32 - 2 * R;              // owned pixels per group
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = p.W, H = p.H, C = p.C;
-    constexpr Smem L = smem_layout(K, NG);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int gi = warp / K, k = warp - gi * K;
     const int b = blockIdx.z;
-    constexpr int OWN = 32 - 2 * R;              // owned pixels per group
     const int group0 = blockIdx.x * NG;          // first pixel group of this CTA
     const int grp = group0 + gi;
     const bool grp_live = grp < p.ngroups;
     const int px = grp * OWN - R + lane;         // this lane's pixel column
     const bool px_in = grp_live && px >= 0 && px < W;
     const bool own_px = px_in && lane >= R && lane < 32 - R;
-    // the right neighbour of the last image column is the pixel itself (g1 = 0 there)
-    const int src_right = (px < W - 1 && lane < 31) ? lane + 1 : lane;
-    const float pxin_f = px_in ? 1.f : 0.f;
 
     const int r0 = blockIdx.y * p.seg_rows;
     const int r1 = min(H, r0 + p.seg_rows);
     const int rs = max(0, r0 - R), rend = r1 + R;       // steps rho in [rs, rend)
     const int load_end = min(H, rend);
     const int nblk = (rend - rs + RB - 1) / RB;
+    // steps whose R stages all work on rows inside [r0, r1) and the image
+    const int fast_lo = r0 + R, fast_hi = min(r1, H - 1);
 
     const size_t frame_b = (size_t)b * H * W * C;        // batch offsets
     const size_t meas_b = (size_t)b * H * W;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
     // ---- producer set-up: every thread owns one 16-byte chunk of x and of Phi per row -----------
-    //      (NG*32*K chunks per row == NT threads) and threads < 3*NG*32 one y/y1/Phi_sum value
+    //      (NG*32*K chunks per row == NT threads) and up to three y/y1/Phi_sum values
     const float* src_x; const float* src_phi; uint32_t dst_tile; int tile_bytes;
     {
         const int g2 = tid / (32 * K);
@@ -124,15 +211,16 @@ gap_tv_stream_kernel(const FusedParams p) {
         dst_tile = smem_base + ((g2 * K + kk) * PADL + ln) * 16;
         tile_bytes = ok ? 16 : 0;
     }
-    const float* src_small[3]; uint32_t dst_small[3]; int small_bytes[3];
+    constexpr int NSMALL = (3 * NG * 32 + NT - 1) / NT;     // y/y1/Phi_sum values per thread
+    const float* src_small[NSMALL]; uint32_t dst_small[NSMALL]; int small_bytes[NSMALL];
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {                       // 3*NG*32 values per row, <= 3 per thread
+    for (int t = 0; t < NSMALL; ++t) {
         const int idx = tid + t * NT;
         const int which = idx / (NG * 32);              // 0: y, 1: y1, 2: Phi_sum
-        const int c = idx - which * NG * 32;
+        const int cidx = idx - which * NG * 32;
         src_small[t] = nullptr; dst_small[t] = 0; small_bytes[t] = 0;
         if (which < 3) {
-            const int g2 = c >> 5, ln = c & 31;
+            const int g2 = cidx >> 5, ln = cidx & 31;
             const int gpx = (group0 + g2) * OWN - R + ln;
             const bool ok = gpx >= 0 && gpx < W && (group0 + g2) < p.ngroups;
             const float* base = which == 0 ? p.y + meas_b
@@ -141,14 +229,14 @@ gap_tv_stream_kernel(const FusedParams p) {
             if (base) {
                 src_small[t] = base + (ok ? gpx : 0);
                 small_bytes[t] = ok ? 4 : 0;
-                dst_small[t] = smem_base + 2 * L.tile_f4_per_row * 16 + (which * NG * 32 + c) * 4;
+                dst_small[t] = smem_base + 2 * L.tile_f4_per_row * 16 + (which * NG * 32 + cidx) * 4;
             }
         }
     }
     const size_t row_f = (size_t)W * C;
     auto issue = [&](int blk) {
         if (blk < nblk) {
-            const uint32_t boff = (blk & 1) * L.buf_bytes;
+            const uint32_t boff = (blk % NSLOT) * L.buf_bytes;
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
                 const int row = rs + blk * RB + j;
@@ -157,44 +245,18 @@ gap_tv_stream_kernel(const FusedParams p) {
                     cp_async16(dst_tile + d, src_x + row * row_f, tile_bytes);
                     cp_async16(dst_tile + d + L.tile_f4_per_row * 16, src_phi + row * row_f, tile_bytes);
 #pragma unroll
-                    for (int t = 0; t < 3; ++t)
+                    for (int t = 0; t < NSMALL; ++t)
                         if (src_small[t]) cp_async4(dst_small[t] + d, src_small[t] + (size_t)row * W, small_bytes[t]);
                 }
             }
         }
         cp_async_commit();
     };
-
-    // ---- pipeline state (registers), channels as two packed pairs ------------------------------------
-    P2 o_prev[R][2], g1_prev[R][2];
-    P2 P0[R + 1][2], P1[R + 1][2];           // P[i] = p^i(rho-i-1); P[0] stays 0
-    P2 fd[R][2];                             // fd[j] = f(rho-1-j)
-    P2 en[R][2];                             // energy partials of iterations 0..R-1
-    const P2 zero2 = splat(0.f);
-#pragma unroll
-    for (int i = 0; i < R; ++i)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) { o_prev[i][c] = zero2; g1_prev[i][c] = zero2; fd[i][c] = zero2; en[i][c] = zero2; }
-#pragma unroll
-    for (int i = 0; i <= R; ++i)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) { P0[i][c] = zero2; P1[i][c] = zero2; }
-
-    const P2 mone2 = splat(-1.f), mtau2 = splat(-0.25f), tvc2 = splat(p.tv_c), one2 = splat(1.f);
-    const float tvw = p.tv_w, lam = p.lambda;
-    float* part = reinterpret_cast<float*>(smem_raw + L.part_off);
-    float* xo = p.x_out + frame_b;
-    float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + meas_b : nullptr;
-
-    issue(0);
-#pragma unroll 1
-    for (int blk = 0; blk < nblk; ++blk) {
-        issue(blk + 1);
-        cp_async_wait<1>();
-        __syncthreads();
-        const unsigned char* buf = smem_raw + (blk & 1) * L.buf_bytes;
-
-        // ---- phase A: partial dot products of this warp's chunk --------------------------------------
+    // partial dot products of this warp's chunk for the rows of block `blk`
+    auto phase_a = [&](int blk) {
+        if (blk >= nblk) return;
+        const unsigned char* buf = smem_raw + (blk % NSLOT) * L.buf_bytes;
+        float* part = reinterpret_cast<float*>(smem_raw + L.part_off + (blk & 1) * L.part_bytes);
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             const int row = rs + blk * RB + j;
@@ -206,119 +268,118 @@ gap_tv_stream_kernel(const FusedParams p) {
                 d = fmaf(xv.z, pv.z, d);
                 d = fmaf(xv.w, pv.w, d);
                 part[((j * NG + gi) * 32 + lane) * L.KP + k] = d;
-                if (k == 0)
+                if (k == 0) {
 #pragma unroll
                     for (int kk = K; kk < L.KP; ++kk) part[((j * NG + gi) * 32 + lane) * L.KP + kk] = 0.f;
+                }
             }
         }
-        __syncthreads();
+    };
 
-        // ---- phase B: RB pipeline steps ------------------------------------------------------------------
+    Pipe<R> S;
+    const P2 zero2 = splat(0.f);
 #pragma unroll
-        for (int j = 0; j < RB; ++j) {
-            const int rho = rs + blk * RB + j;
-            if (rho < rend) {
-                P2 f_new[2] = {zero2, zero2};
-                if (rho < H) {
-                    // stage 0: Euclidean projection of row rho
-                    const unsigned char* rowp = buf + j * L.row_bytes;
-                    const float4* tx = reinterpret_cast<const float4*>(rowp) + (gi * K + k) * PADL + lane;
-                    const float4 xv = tx[0], pv = tx[L.tile_f4_per_row];
-                    const float4* pp = reinterpret_cast<const float4*>(part + ((j * NG + gi) * 32 + lane) * L.KP);
-                    float yb = 0.f;
+    for (int i = 0; i < R; ++i)
 #pragma unroll
-                    for (int q = 0; q < L.KP / 4; ++q) { const float4 t = pp[q]; yb += (t.x + t.y) + (t.z + t.w); }
-                    const float* sm = reinterpret_cast<const float*>(rowp + 2 * L.tile_f4_per_row * 16);
-                    const float yv = sm[gi * 32 + lane];
-                    const float psv = sm[2 * NG * 32 + gi * 32 + lane];
-                    float s;
-                    if (MODE == MODE_GAP_ACC) {
-                        const float y1n = sm[NG * 32 + gi * 32 + lane] + (yv - yb);
-                        if (k == 0 && own_px && rho >= r0 && rho < r1) y1o[(size_t)rho * W + px] = y1n;
-                        s = __fdividef(y1n - yb, psv);
-                    } else {
-                        s = __fdividef(yv - yb, psv);
-                    }
-                    const P2 s2 = splat(px_in ? s * lam : 0.f);
-                    f_new[0] = fma2(s2, make_float2(pv.x, pv.y), make_float2(xv.x, xv.y));
-                    f_new[1] = fma2(s2, make_float2(pv.z, pv.w), make_float2(xv.z, xv.w));
+        for (int q = 0; q < 2; ++q) { S.o_prev[i][q] = zero2; S.g1_prev[i][q] = zero2; S.fd[i][q] = zero2; S.en[i][q] = zero2; }
+#pragma unroll
+    for (int i = 0; i <= R; ++i)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { S.P0[i][q] = zero2; S.P1[i][q] = zero2; }
+
+    StepConst sc;
+    sc.mone2 = splat(-1.f); sc.mtau2 = splat(-0.25f); sc.tvc2 = splat(p.tv_c); sc.one2 = splat(1.f);
+    sc.tvw = p.tv_w; sc.wm2 = splat(p.tv_w);
+    sc.own_f = own_px ? 1.f : 0.f; sc.pxin_f = px_in ? 1.f : 0.f;
+    // the right neighbour of the last image column is the pixel itself (g1 = 0 there)
+    // (and of any lane outside the image, whose state then stays identically zero)
+    sc.src_right = (px_in && px < W - 1 && lane < 31) ? lane + 1 : lane;
+    sc.rs = rs; sc.r0 = r0; sc.r1 = r1; sc.H = H;
+    const float lam = p.lambda;
+    float* xo = p.x_out + frame_b;
+    float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + meas_b : nullptr;
+
+    // stage 0 of step rho (row j of the block in `buf`): Euclidean projection -> f(rho)
+    auto project_row = [&](const unsigned char* buf, const float* part, int j, int rho, P2 (&f_new)[2]) {
+        const unsigned char* rowp = buf + j * L.row_bytes;
+        const float4* tx = reinterpret_cast<const float4*>(rowp) + (gi * K + k) * PADL + lane;
+        const float4 xv = tx[0], pv = tx[L.tile_f4_per_row];
+        const float4* pp = reinterpret_cast<const float4*>(part + ((j * NG + gi) * 32 + lane) * L.KP);
+        float yb = 0.f;
+#pragma unroll
+        for (int q = 0; q < L.KP / 4; ++q) { const float4 t = pp[q]; yb += (t.x + t.y) + (t.z + t.w); }
+        const float* sm = reinterpret_cast<const float*>(rowp + 2 * L.tile_f4_per_row * 16);
+        const float yv = sm[gi * 32 + lane];
+        const float psv = sm[2 * NG * 32 + gi * 32 + lane];
+        float s;
+        if (MODE == MODE_GAP_ACC) {
+            const float y1n = sm[NG * 32 + gi * 32 + lane] + (yv - yb);
+            if (k == 0 && own_px && rho >= r0 && rho < r1) y1o[(size_t)rho * W + px] = y1n;
+            s = __fdividef(y1n - yb, psv);
+        } else {
+            s = __fdividef(yv - yb, psv);
+        }
+        const P2 s2 = splat(px_in ? s * lam : 0.f);
+        f_new[0] = fma2(s2, make_float2(pv.x, pv.y), make_float2(xv.x, xv.y));
+        f_new[1] = fma2(s2, make_float2(pv.z, pv.w), make_float2(xv.z, xv.w));
+    };
+    auto store_row = [&](int orow, const P2 (&o)[2]) {
+        if (own_px && orow >= r0 && orow < r1)
+            *reinterpret_cast<float4*>(xo + ((size_t)orow * W + px) * C + 4 * k) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+    };
+
+    issue(0);
+    issue(1);
+    cp_async_wait<1>();
+    __syncthreads();
+    phase_a(0);
+#pragma unroll 1
+    for (int blk = 0; blk < nblk; ++blk) {
+        // one barrier per block: block blk+1 has landed, the partials of block blk are visible,
+        // and everybody is done with slot (blk+2)%3 (last read in the previous iteration)
+        cp_async_wait<0>();
+        __syncthreads();
+        issue(blk + 2);
+        phase_a(blk + 1);
+        const unsigned char* buf = smem_raw + (blk % NSLOT) * L.buf_bytes;
+        const float* part = reinterpret_cast<const float*>(smem_raw + L.part_off + (blk & 1) * L.part_bytes);
+        const int rho0 = rs + blk * RB;
+        if (rho0 >= fast_lo && rho0 + RB - 1 <= fast_hi) {
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                const int rho = rho0 + j;
+                P2 f_new[2], o_new[2];
+                project_row(buf, part, j, rho, f_new);
+                pipe_step<R, CHECK, true>(S, sc, rho, f_new, o_new);
+                store_row(rho - R, o_new);
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < RB; ++j) {
+                const int rho = rho0 + j;
+                if (rho < rend) {
+                    P2 f_new[2] = {zero2, zero2}, o_new[2];
+                    if (rho < H) project_row(buf, part, j, rho, f_new);
+                    pipe_step<R, CHECK, false>(S, sc, rho, f_new, o_new);
+                    store_row(rho - R, o_new);
                 }
-                P2 o_new[2] = {f_new[0], f_new[1]};
-                P2 pend0[2], pend1[2];
-#pragma unroll
-                for (int i = 0; i < R; ++i) {
-                    const int row_new = rho - i;          // row of o_new = out_i(row_new)
-                    const int u = row_new - 1;            // row whose dual variable advances
-                    // masks as multipliers: the dual variable of a row outside the segment/image or of
-                    // a pixel outside the image stays 0; g0 = 0 below the last image row
-                    const P2 m2 = splat(((u >= rs) && (u < H)) ? pxin_f : 0.f);
-                    const P2 md2 = splat(row_new < H ? 1.f : 0.f);
-                    const float me = (CHECK && own_px && u >= r0 && u < r1) ? 1.f : 0.f;
-                    const P2 me2 = splat(me), wm2 = splat(me * tvw);
-                    P2 pi0[2], pi1[2];
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) { pi0[c] = P0[i][c]; pi1[c] = P1[i][c]; }
-                    if (i > 0) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) { P0[i][c] = pend0[c]; P1[i][c] = pend1[c]; }
-                    }
-                    P2 o_next[2];
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const P2 o_right = shfl_idx2(o_new[c], src_right);
-                        const P2 g0 = mul2(fma2(o_prev[i][c], mone2, o_new[c]), md2);
-                        const P2 g1 = g1_prev[i][c];
-                        const P2 nrm = sqrt2(fma2(g0, g0, mul2(g1, g1)));
-                        const P2 r = mul2(rcp2(fma2(nrm, tvc2, one2)), m2);
-                        const P2 pn0 = mul2(fma2(g0, mtau2, pi0[c]), r);
-                        const P2 pn1 = mul2(fma2(g1, mtau2, pi1[c]), r);
-                        const P2 p1l = shfl_up2(pn1);
-                        // D(p^{i+1})(u) = (p0(u-1) - p0(u)) + (p1(u, left) - p1(u))
-                        const P2 d = add2(fma2(pn0, mone2, P0[i + 1][c]), fma2(pn1, mone2, p1l));
-                        o_next[c] = add2(fd[i][c], d);
-                        if (CHECK) {
-                            en[i][c] = fma2(nrm, wm2, en[i][c]);                        // w*|grad out_i|(u)
-                            if (i + 1 < R) en[i + 1][c] = fma2(mul2(d, me2), d, en[i + 1][c]);   // D(p^{i+1})(u)^2
-                        }
-                        g1_prev[i][c] = fma2(o_new[c], mone2, o_right);
-                        o_prev[i][c] = o_new[c];
-                        pend0[c] = pn0;
-                        pend1[c] = pn1;
-                    }
-                    o_new[0] = o_next[0];
-                    o_new[1] = o_next[1];
-                }
-#pragma unroll
-                for (int c = 0; c < 2; ++c) { P0[R][c] = pend0[c]; P1[R][c] = pend1[c]; }
-                // f delay line
-#pragma unroll
-                for (int i = R - 1; i > 0; --i) { fd[i][0] = fd[i - 1][0]; fd[i][1] = fd[i - 1][1]; }
-                fd[0][0] = f_new[0];
-                fd[0][1] = f_new[1];
-                // out_R(rho-R) leaves the pipeline
-                const int orow = rho - R;
-                if (own_px && orow >= r0 && orow < r1)
-                    *reinterpret_cast<float4*>(xo + ((size_t)orow * W + px) * C + 4 * k) =
-                        make_float4(o_new[0].x, o_new[0].y, o_new[1].x, o_new[1].y);
             }
         }
-        __syncthreads();
     }
 
     if (CHECK) {
-        // reduce the energy partials over the pixels of the warp, one atomic per (channel, i)
+        // reduce the energy partials over the owned pixels of the warp, one atomic per (channel, i)
 #pragma unroll
         for (int i = 0; i < R; ++i)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float v = (c & 1) ? en[i][c >> 1].y : en[i][c >> 1].x;
+            for (int ch = 0; ch < 4; ++ch) {
+                float v = ((ch & 1) ? S.en[i][ch >> 1].y : S.en[i][ch >> 1].x) * sc.own_f;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0 && grp_live) atomicAdd(p.energy + ((size_t)b * C + 4 * k + c) * R + i, (double)v);
+                if (lane == 0 && grp_live) atomicAdd(p.energy + ((size_t)b * C + 4 * k + ch) * R + i, (double)v);
             }
     }
 }
-
 
 // one launcher per R, defined in fused_inst_r{2,3,4}.cu
 template <int R> int launch_stream_r(int mode, int K, const FusedParams& fp, dim3 grid, cudaStream_t st);
