@@ -49,6 +49,56 @@ __global__ void energy_check_kernel(const double* __restrict__ energy, int nslic
     }
 }
 
+// ---- TMA descriptors -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// frame stack [rows][W][K][4 floats] -> boxes of RB rows x 32 pixels x 1 chunk x 4 floats
+int make_frame_map(CUtensorMap* tm, const float* base, long long rows, int W, int C) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SCIPNP_ECUDA; }
+    cuuint64_t dims[4] = {4, (cuuint64_t)(C / 4), (cuuint64_t)W, (cuuint64_t)rows};
+    cuuint64_t strides[3] = {16, (cuuint64_t)C * 4, (cuuint64_t)W * C * 4};
+    cuuint32_t box[4] = {4, 1, 32, (cuuint32_t)RB};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(frame) failed with CUresult %d", (int)r); return SCIPNP_ECUDA; }
+    return SCIPNP_OK;
+}
+
+// measurement plane [rows][W] -> boxes of RB rows x 32 pixels
+int make_plane_map(CUtensorMap* tm, const float* base, long long rows, int W) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SCIPNP_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)W * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)RB};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(plane) failed with CUresult %d", (int)r); return SCIPNP_ECUDA; }
+    return SCIPNP_OK;
+}
+
 }  // namespace
 
 bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max) {
@@ -107,15 +157,33 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     nseg = (a.H + fp.seg_rows - 1) / fp.seg_rows;
     fp.phi_bstride = a.phi_batched ? (long long)a.H * a.W * a.C : 0;
     fp.ps_bstride = a.phi_batched ? (long long)a.H * a.W : 0;
+    fp.phi_batched = a.phi_batched ? 1 : 0;
     if (nseg > 65535) { set_error("too many row segments"); return SCIPNP_EINVAL; }
     dim3 grid(gx, (unsigned)nseg, a.B);
+
+    // TMA descriptors of this launch (x ping-pongs, so they are rebuilt per call: ~1 us each on the host)
+    alignas(64) FusedMaps maps;
+    const long long rows = (long long)a.B * a.H, phi_rows = a.phi_batched ? rows : a.H;
+    if (int e = make_frame_map(&maps.x, a.x_in, rows, a.W, a.C)) return e;
+    if (int e = make_frame_map(&maps.phi, a.Phi, phi_rows, a.W, a.C)) return e;
+    // plane boxes start at pixel grp*(32-2R) - R: the TMA unit needs that start 16-byte aligned,
+    // which holds for R = 4 (tv_iter_max = 5, the reference's setting); otherwise cp.async
+    fp.small_tma = (a.W % 4 == 0) && (R % 4 == 0) && aligned16(a.y) && aligned16(a.Phi_sum) &&
+                   (a.mode != MODE_GAP_ACC || aligned16(a.y1_in));
+    if (fp.small_tma) {
+        if (int e = make_plane_map(&maps.y, a.y, rows, a.W)) return e;
+        if (int e = make_plane_map(&maps.ps, a.Phi_sum, phi_rows, a.W)) return e;
+        if (int e = make_plane_map(&maps.y1, a.mode == MODE_GAP_ACC ? a.y1_in : a.y, rows, a.W)) return e;
+    } else {
+        maps.y = maps.x; maps.ps = maps.x; maps.y1 = maps.x;    // unused
+    }
 
     SCIPNP_CUDA(cudaMemsetAsync(fp.energy, 0, (size_t)a.B * a.C * R * sizeof(double), st));
     int rc = SCIPNP_OK;
     switch (R) {
-        case 2: rc = launch_stream_r<2>(a.mode, fp.K, fp, grid, st); break;
-        case 3: rc = launch_stream_r<3>(a.mode, fp.K, fp, grid, st); break;
-        case 4: rc = launch_stream_r<4>(a.mode, fp.K, fp, grid, st); break;
+        case 2: rc = launch_stream_r<2>(a.mode, fp.K, fp, maps, grid, st); break;
+        case 3: rc = launch_stream_r<3>(a.mode, fp.K, fp, maps, grid, st); break;
+        case 4: rc = launch_stream_r<4>(a.mode, fp.K, fp, maps, grid, st); break;
         default: set_error("unsupported tv_iter_max"); return SCIPNP_EINVAL;
     }
     if (rc) return rc;

@@ -1,6 +1,8 @@
 // Kernel template of the one-pass fused GAP-TV iteration (see gap_tv_fused.cu for the
 // design notes).  Included by the per-R instantiation units fused_inst_r*.cu.
 #pragma once
+#include <cuda.h>
+
 #include "internal.cuh"
 
 namespace scipnp {
@@ -8,7 +10,7 @@ namespace fusedk {
 
 constexpr int RB = 4;             // rows per staged block
 constexpr int NSLOT = 3;          // staging ring: block b in slot b % 3
-constexpr int PADL = 33;          // padded lane stride of the transposed tiles (float4 units)
+constexpr int BOX_BYTES = RB * 32 * 16;   // one TMA box: RB rows x 32 pixels x one 4-channel chunk
 constexpr int kMaxWarps = 8;
 
 struct FusedParams {
@@ -19,40 +21,77 @@ struct FusedParams {
     float lambda, tv_c, tv_w;     // tv_c = tau / weight
     int H, W, C, K, NG, ngroups;  // K = C/4 chunk-warps per pixel group, NG groups per CTA
     int seg_rows;
+    int small_tma;                // y / y1 / Phi_sum rows staged by TMA (needs W % 4 == 0), else cp.async
+    int phi_batched;
     long long phi_bstride, ps_bstride;   // batch strides (0 when shared)
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
+// tensor maps of one launch: x_in and Phi as [rows][W][K][4 floats] (box RB x 32 x 1 x 4, i.e. the
+// transposition to chunk-major tiles is done by the TMA unit), y / y1_in / Phi_sum as [rows][W]
+struct FusedMaps { CUtensorMap x, phi, y, y1, ps; };
+
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// ---- TMA + mbarrier (inline PTX) ---------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
 __device__ __forceinline__ float fast_sqrt(float v) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float fast_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 
-// shared-memory carve-up (per CTA), all offsets in bytes
+// shared-memory carve-up (per CTA), all offsets in bytes.  One staging slot holds RB rows:
+//   x   tiles [NG][K][RB][32] float4   (one TMA box per (group, chunk))
+//   Phi tiles [NG][K][RB][32] float4
+//   y, y1, Phi_sum  [3][NG][RB][32] float
 struct Smem {
-    int tile_f4_per_row;     // float4 slots of one of {x, Phi} for one row: NG*K*PADL
-    int row_bytes;           // one staged row: 2 tiles + y, y1, Phi_sum lanes
-    int buf_bytes;           // RB rows
+    int tile_bytes;          // all x (or all Phi) boxes of a slot: NG*K*BOX_BYTES
+    int small_off;           // offset of the y/y1/Phi_sum rows inside a slot
+    int buf_bytes;           // one slot
     int part_off;            // partial dot products, two buffers of [RB][NG][32][KP]
     int part_bytes;
+    int bar_off;             // NSLOT mbarriers
     int KP;
     int total;
 };
 __host__ __device__ constexpr Smem smem_layout(int K, int NG) {
     Smem s{};
-    s.tile_f4_per_row = NG * K * PADL;
-    s.row_bytes = 2 * s.tile_f4_per_row * 16 + 3 * NG * 32 * 4;
-    s.buf_bytes = RB * s.row_bytes;
+    s.tile_bytes = NG * K * BOX_BYTES;
+    s.small_off = 2 * s.tile_bytes;
+    s.buf_bytes = s.small_off + 3 * NG * RB * 32 * 4;
     s.KP = (K + 3) & ~3;
     s.part_off = NSLOT * s.buf_bytes;
     s.part_bytes = RB * NG * 32 * s.KP * 4;
-    s.total = s.part_off + 2 * s.part_bytes;
+    s.bar_off = s.part_off + 2 * s.part_bytes;
+    s.total = s.bar_off + 64;
     return s;
 }
 
@@ -166,12 +205,12 @@ __device__ __forceinline__ void pipe_step(Pipe<R>& S, const StepConst& c, int rh
 
 template <int R, int MODE, bool CHECK, int K>
 __global__ void __launch_bounds__(fused_threads(K), 2)
-gap_tv_stream_kernel(const FusedParams p) {
+gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps) {
     constexpr int NG = fused_groups(K);
     constexpr int NT = fused_threads(K);
     constexpr Smem L = smem_layout(K, NG);
     constexpr int OWN = 32 - 2 * R;              // owned pixels per group
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = p.W, H = p.H, C = p.C;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -196,82 +235,89 @@ gap_tv_stream_kernel(const FusedParams p) {
     const size_t meas_b = (size_t)b * H * W;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
-    // ---- producer set-up: every thread owns one 16-byte chunk of x and of Phi per row -----------
-    //      (NG*32*K chunks per row == NT threads) and up to three y/y1/Phi_sum values
-    const float* src_x; const float* src_phi; uint32_t dst_tile; int tile_bytes;
-    {
-        const int g2 = tid / (32 * K);
-        const int rem = tid - g2 * 32 * K;
-        const int ln = rem / K, kk = rem - ln * K;
-        const int gpx = (group0 + g2) * OWN - R + ln;
-        const bool ok = gpx >= 0 && gpx < W && (group0 + g2) < p.ngroups;
-        const size_t off = (size_t)(ok ? gpx : 0) * C + 4 * kk;
-        src_x = p.x_in + frame_b + off;
-        src_phi = p.Phi + (size_t)b * p.phi_bstride + off;
-        dst_tile = smem_base + ((g2 * K + kk) * PADL + ln) * 16;
-        tile_bytes = ok ? 16 : 0;
-    }
-    constexpr int NSMALL = (3 * NG * 32 + NT - 1) / NT;     // y/y1/Phi_sum values per thread
-    const float* src_small[NSMALL]; uint32_t dst_small[NSMALL]; int small_bytes[NSMALL];
-#pragma unroll
-    for (int t = 0; t < NSMALL; ++t) {
-        const int idx = tid + t * NT;
-        const int which = idx / (NG * 32);              // 0: y, 1: y1, 2: Phi_sum
-        const int cidx = idx - which * NG * 32;
-        src_small[t] = nullptr; dst_small[t] = 0; small_bytes[t] = 0;
-        if (which < 3) {
-            const int g2 = cidx >> 5, ln = cidx & 31;
-            const int gpx = (group0 + g2) * OWN - R + ln;
-            const bool ok = gpx >= 0 && gpx < W && (group0 + g2) < p.ngroups;
-            const float* base = which == 0 ? p.y + meas_b
-                              : which == 1 ? (MODE == MODE_GAP_ACC ? p.y1_in + meas_b : nullptr)
-                                           : p.Phi_sum + (size_t)b * p.ps_bstride;
-            if (base) {
-                src_small[t] = base + (ok ? gpx : 0);
-                small_bytes[t] = ok ? 4 : 0;
-                dst_small[t] = smem_base + 2 * L.tile_f4_per_row * 16 + (which * NG * 32 + cidx) * 4;
-            }
-        }
-    }
-    const size_t row_f = (size_t)W * C;
+    // ---- producer: thread 0 programs the TMA unit, RB rows per block ------------------------------
+    //      2*NG*K boxes of x / Phi (+ 3*NG rows of y, y1, Phi_sum) land in slot blk % 3 and
+    //      complete on that slot's mbarrier.  Pixels left/right of the image are zero-filled by
+    //      the TMA unit; rows past the segment are loaded but never used.
+    const uint32_t bar_base = smem_base + L.bar_off;
+    constexpr uint32_t kTileTx = 2u * NG * K * BOX_BYTES;
+    constexpr uint32_t kSmallTx = (MODE == MODE_GAP_ACC ? 3u : 2u) * NG * RB * 32 * 4;
+    const int rowc0 = b * H;                              // row coordinate of the batch element
+    const int phirow0 = p.phi_batched ? b * H : 0;
+    // cp.async fallback for the y / y1 / Phi_sum rows when W % 4 != 0 (TMA needs 16-byte row pitch)
+    constexpr int NSMALL = (3 * NG * RB * 32 + NT - 1) / NT;
     auto issue = [&](int blk) {
         if (blk < nblk) {
-            const uint32_t boff = (blk % NSLOT) * L.buf_bytes;
+            const int slot = blk % NSLOT;
+            const uint32_t dst = smem_base + slot * L.buf_bytes;
+            const int row0 = rs + blk * RB;
+            if (tid == 0) {
+                const uint32_t bar = bar_base + slot * 8;
+                mbar_expect_tx(bar, kTileTx + (p.small_tma ? kSmallTx : 0u));
+#pragma unroll 1
+                for (int g2 = 0; g2 < NG; ++g2) {
+                    const int px0 = (group0 + g2) * OWN - R;
+#pragma unroll 1
+                    for (int kk = 0; kk < K; ++kk) {
+                        const uint32_t d = dst + (g2 * K + kk) * BOX_BYTES;
+                        tma_load_4d(d, &maps.x, 0, kk, px0, rowc0 + row0, bar);
+                        tma_load_4d(d + L.tile_bytes, &maps.phi, 0, kk, px0, phirow0 + row0, bar);
+                    }
+                    if (p.small_tma) {
+                        const uint32_t ds = dst + L.small_off + g2 * RB * 128;
+                        tma_load_2d(ds, &maps.y, px0, rowc0 + row0, bar);
+                        if (MODE == MODE_GAP_ACC) tma_load_2d(ds + NG * RB * 128, &maps.y1, px0, rowc0 + row0, bar);
+                        tma_load_2d(ds + 2 * NG * RB * 128, &maps.ps, px0, phirow0 + row0, bar);
+                    }
+                }
+            }
+            if (!p.small_tma) {
 #pragma unroll
-            for (int j = 0; j < RB; ++j) {
-                const int row = rs + blk * RB + j;
-                if (row < load_end) {
-                    const uint32_t d = boff + j * L.row_bytes;
-                    cp_async16(dst_tile + d, src_x + row * row_f, tile_bytes);
-                    cp_async16(dst_tile + d + L.tile_f4_per_row * 16, src_phi + row * row_f, tile_bytes);
-#pragma unroll
-                    for (int t = 0; t < NSMALL; ++t)
-                        if (src_small[t]) cp_async4(dst_small[t] + d, src_small[t] + (size_t)row * W, small_bytes[t]);
+                for (int t = 0; t < NSMALL; ++t) {
+                    const int idx = tid + t * NT;                 // [which][g2][j][lane]
+                    const int which = idx / (NG * RB * 32);
+                    const int rem = idx - which * NG * RB * 32;
+                    const int g2 = rem / (RB * 32), j = (rem >> 5) % RB, ln = rem & 31;
+                    const int gpx = (group0 + g2) * OWN - R + ln;
+                    const int row = row0 + j;
+                    const bool ok = which < 3 && gpx >= 0 && gpx < W && row < H && (group0 + g2) < p.ngroups &&
+                                    !(which == 1 && MODE != MODE_GAP_ACC);
+                    if (which < 3) {
+                        const float* base = which == 0 ? p.y + meas_b
+                                          : which == 1 ? (MODE == MODE_GAP_ACC ? p.y1_in + meas_b : p.y + meas_b)
+                                                       : p.Phi_sum + (size_t)b * p.ps_bstride;
+                        cp_async4(dst + L.small_off + idx * 4, base + (ok ? (size_t)row * W + gpx : 0), ok ? 4 : 0);
+                    }
                 }
             }
         }
-        cp_async_commit();
+        if (!p.small_tma) cp_async_commit();
+    };
+    auto wait_block = [&](int blk) {       // tiles (and TMA-staged rows) of block blk have landed
+        if (blk < nblk) mbar_wait(bar_base + (blk % NSLOT) * 8, (blk / NSLOT) & 1);
     };
     // partial dot products of this warp's chunk for the rows of block `blk`
     auto phase_a = [&](int blk) {
         if (blk >= nblk) return;
         const unsigned char* buf = smem_raw + (blk % NSLOT) * L.buf_bytes;
         float* part = reinterpret_cast<float*>(smem_raw + L.part_off + (blk & 1) * L.part_bytes);
+        float4 xv[RB], pv[RB];
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {           // all loads first: one shared-memory round trip
+            const float4* tx = reinterpret_cast<const float4*>(buf + (gi * K + k) * BOX_BYTES) + j * 32 + lane;
+            xv[j] = tx[0];
+            pv[j] = tx[L.tile_bytes / 16];
+        }
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
-            const int row = rs + blk * RB + j;
-            if (row < load_end) {
-                const float4* tx = reinterpret_cast<const float4*>(buf + j * L.row_bytes) + (gi * K + k) * PADL + lane;
-                const float4 xv = tx[0], pv = tx[L.tile_f4_per_row];
-                float d = xv.x * pv.x;
-                d = fmaf(xv.y, pv.y, d);
-                d = fmaf(xv.z, pv.z, d);
-                d = fmaf(xv.w, pv.w, d);
-                part[((j * NG + gi) * 32 + lane) * L.KP + k] = d;
-                if (k == 0) {
+            float d = xv[j].x * pv[j].x;
+            d = fmaf(xv[j].y, pv[j].y, d);
+            d = fmaf(xv[j].z, pv[j].z, d);
+            d = fmaf(xv[j].w, pv[j].w, d);
+            part[((j * NG + gi) * 32 + lane) * L.KP + k] = d;
+            if (k == 0) {
 #pragma unroll
-                    for (int kk = K; kk < L.KP; ++kk) part[((j * NG + gi) * 32 + lane) * L.KP + kk] = 0.f;
-                }
+                for (int kk = K; kk < L.KP; ++kk) part[((j * NG + gi) * 32 + lane) * L.KP + kk] = 0.f;
             }
         }
     };
@@ -301,19 +347,18 @@ gap_tv_stream_kernel(const FusedParams p) {
 
     // stage 0 of step rho (row j of the block in `buf`): Euclidean projection -> f(rho)
     auto project_row = [&](const unsigned char* buf, const float* part, int j, int rho, P2 (&f_new)[2]) {
-        const unsigned char* rowp = buf + j * L.row_bytes;
-        const float4* tx = reinterpret_cast<const float4*>(rowp) + (gi * K + k) * PADL + lane;
-        const float4 xv = tx[0], pv = tx[L.tile_f4_per_row];
+        const float4* tx = reinterpret_cast<const float4*>(buf + (gi * K + k) * BOX_BYTES) + j * 32 + lane;
+        const float4 xv = tx[0], pv = tx[L.tile_bytes / 16];
         const float4* pp = reinterpret_cast<const float4*>(part + ((j * NG + gi) * 32 + lane) * L.KP);
         float yb = 0.f;
 #pragma unroll
         for (int q = 0; q < L.KP / 4; ++q) { const float4 t = pp[q]; yb += (t.x + t.y) + (t.z + t.w); }
-        const float* sm = reinterpret_cast<const float*>(rowp + 2 * L.tile_f4_per_row * 16);
-        const float yv = sm[gi * 32 + lane];
-        const float psv = sm[2 * NG * 32 + gi * 32 + lane];
+        const float* sm = reinterpret_cast<const float*>(buf + L.small_off) + (gi * RB + j) * 32 + lane;
+        const float yv = sm[0];
+        const float psv = sm[2 * NG * RB * 32];
         float s;
         if (MODE == MODE_GAP_ACC) {
-            const float y1n = sm[NG * 32 + gi * 32 + lane] + (yv - yb);
+            const float y1n = sm[NG * RB * 32] + (yv - yb);
             if (k == 0 && own_px && rho >= r0 && rho < r1) y1o[(size_t)rho * W + px] = y1n;
             s = __fdividef(y1n - yb, psv);
         } else {
@@ -328,18 +373,25 @@ gap_tv_stream_kernel(const FusedParams p) {
             *reinterpret_cast<float4*>(xo + ((size_t)orow * W + px) * C + 4 * k) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
 
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NSLOT; ++i) mbar_init(bar_base + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
     issue(0);
     issue(1);
-    cp_async_wait<1>();
-    __syncthreads();
+    wait_block(0);
     phase_a(0);
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
         // one barrier per block: block blk+1 has landed, the partials of block blk are visible,
         // and everybody is done with slot (blk+2)%3 (last read in the previous iteration)
-        cp_async_wait<0>();
+        if (!p.small_tma) cp_async_wait<0>();
         __syncthreads();
         issue(blk + 2);
+        wait_block(blk + 1);
         phase_a(blk + 1);
         const unsigned char* buf = smem_raw + (blk % NSLOT) * L.buf_bytes;
         const float* part = reinterpret_cast<const float*>(smem_raw + L.part_off + (blk & 1) * L.part_bytes);
@@ -382,40 +434,40 @@ gap_tv_stream_kernel(const FusedParams p) {
 }
 
 // one launcher per R, defined in fused_inst_r{2,3,4}.cu
-template <int R> int launch_stream_r(int mode, int K, const FusedParams& fp, dim3 grid, cudaStream_t st);
+template <int R> int launch_stream_r(int mode, int K, const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st);
 
 template <int R, int MODE, int K>
-int launch_stream_k(const FusedParams& fp, dim3 grid, cudaStream_t st) {
+int launch_stream_k(const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st) {
     auto kfn = gap_tv_stream_kernel<R, MODE, true, K>;
     constexpr Smem L = smem_layout(K, fused_groups(K));
     SCIPNP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    kfn<<<grid, fused_threads(K), L.total, st>>>(fp);
+    kfn<<<grid, fused_threads(K), L.total, st>>>(fp, maps);
     return SCIPNP_OK;
 }
 
 template <int R, int MODE>
-int launch_stream_mode(int K, const FusedParams& fp, dim3 grid, cudaStream_t st) {
+int launch_stream_mode(int K, const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st) {
     switch (K) {
 #ifndef SCIPNP_FUSED_FAST_BUILD
-        case 1: return launch_stream_k<R, MODE, 1>(fp, grid, st);
-        case 3: return launch_stream_k<R, MODE, 3>(fp, grid, st);
-        case 4: return launch_stream_k<R, MODE, 4>(fp, grid, st);
-        case 5: return launch_stream_k<R, MODE, 5>(fp, grid, st);
-        case 7: return launch_stream_k<R, MODE, 7>(fp, grid, st);
-        case 8: return launch_stream_k<R, MODE, 8>(fp, grid, st);
+        case 1: return launch_stream_k<R, MODE, 1>(fp, maps, grid, st);
+        case 3: return launch_stream_k<R, MODE, 3>(fp, maps, grid, st);
+        case 4: return launch_stream_k<R, MODE, 4>(fp, maps, grid, st);
+        case 5: return launch_stream_k<R, MODE, 5>(fp, maps, grid, st);
+        case 7: return launch_stream_k<R, MODE, 7>(fp, maps, grid, st);
+        case 8: return launch_stream_k<R, MODE, 8>(fp, maps, grid, st);
 #endif
-        case 2: return launch_stream_k<R, MODE, 2>(fp, grid, st);
-        case 6: return launch_stream_k<R, MODE, 6>(fp, grid, st);
+        case 2: return launch_stream_k<R, MODE, 2>(fp, maps, grid, st);
+        case 6: return launch_stream_k<R, MODE, 6>(fp, maps, grid, st);
     }
     set_error("fused kernel not built for C = %d", 4 * K);
     return SCIPNP_EINVAL;
 }
 
 #define SCIPNP_INSTANTIATE_FUSED_R(RR)                                                                 \
-    template <> int launch_stream_r<RR>(int mode, int K, const FusedParams& fp, dim3 grid,             \
-                                        cudaStream_t st) {                                             \
-        if (mode == MODE_GAP_ACC) return launch_stream_mode<RR, MODE_GAP_ACC>(K, fp, grid, st);       \
-        return launch_stream_mode<RR, MODE_GAP_PLAIN>(K, fp, grid, st);                                \
+    template <> int launch_stream_r<RR>(int mode, int K, const FusedParams& fp, const FusedMaps& maps, \
+                                        dim3 grid, cudaStream_t st) {                                  \
+        if (mode == MODE_GAP_ACC) return launch_stream_mode<RR, MODE_GAP_ACC>(K, fp, maps, grid, st); \
+        return launch_stream_mode<RR, MODE_GAP_PLAIN>(K, fp, maps, grid, st);                          \
     }
 
 }  // namespace fusedk
