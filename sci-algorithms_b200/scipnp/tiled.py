@@ -1,0 +1,198 @@
+"""Row-tiled GAP-TV over several GPUs (one process per GPU, ``torch.distributed``).
+
+A single scene [H, W, C] is split into contiguous row blocks, one per rank.
+Each rank keeps ``halo = k*(tv_iter_max-1)`` extra rows above and below its
+block and runs the ordinary single-GPU solver on its local rows.  One outer
+iteration moves information by at most ``tv_iter_max-1`` rows (the TV stencil;
+the projection is pointwise), so after ``k`` local iterations exactly the halo
+rows are stale while the owned rows are still identical to the single-GPU
+result.  Every ``k`` iterations the ranks then refresh their halo rows of ``x``
+and ``y1`` from the neighbours that own them (ring-neighbour send/recv, no
+global collective).  Chambolle's boundary rules apply at the true image edges
+only; a tile seam is never treated as an edge for owned rows.
+
+The reference has no counterpart (it is single-process); this is SURVEY.md
+section 8(e) "single UHD scene".
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["partition_rows", "exchange_halos", "TiledSolver", "tiled_reference_run"]
+
+
+def partition_rows(H, world, rank, halo):
+    """Rows owned by ``rank`` ([lo, hi)) and rows held locally ([row_lo, row_hi))."""
+    base, rem = divmod(H, world)
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi, max(0, lo - halo), min(H, hi + halo)
+
+
+def _plan(H, world, halo):
+    return [partition_rows(H, world, r, halo) for r in range(world)]
+
+
+def exchange_halos(fields, H, halo, rank, world, group=None):
+    """Refresh the halo rows of every tensor in ``fields`` (axis 0 = local rows of this rank).
+
+    Every rank derives all partitions from (H, world, halo), so no metadata travels.  Halos
+    may span more than one neighbour when blocks are shorter than ``halo``: the loop below
+    sends each remote rank exactly the intersection of its halo with this rank's owned rows."""
+    if world == 1:
+        return
+    plan = _plan(H, world, halo)
+    lo, hi, row_lo, row_hi = plan[rank]
+    ops, bufs = [], []
+    # gloo moves host memory: stage device rows through the host there (tests); NCCL sends
+    # device rows directly over NVLink
+    via_host = dist.get_backend(group) == "gloo" and any(f.is_cuda for f in fields)
+    for other in range(world):
+        if other == rank:
+            continue
+        olo, ohi, orow_lo, orow_hi = plan[other]
+        # rows I own that `other` holds as halo
+        s0, s1 = max(lo, orow_lo), min(hi, orow_hi)
+        # rows `other` owns that I hold as halo
+        r0, r1 = max(olo, row_lo), min(ohi, row_hi)
+        for f in fields:
+            if s1 > s0:
+                t = f[s0 - row_lo:s1 - row_lo].contiguous()
+                if via_host:
+                    t = t.cpu()
+                bufs.append(t)
+                ops.append(dist.P2POp(dist.isend, t, other, group))
+            if r1 > r0:
+                t = torch.empty_like(f[r0 - row_lo:r1 - row_lo], device="cpu" if via_host else f.device)
+                bufs.append((t, f, r0 - row_lo, r1 - row_lo))
+                ops.append(dist.P2POp(dist.irecv, t, other, group))
+    if not ops:
+        return
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for b in bufs:
+        if isinstance(b, tuple):
+            t, f, a, z = b
+            f[a:z].copy_(t)
+
+
+class _DevView:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4",
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+def _wrap(ptr, shape, device):
+    return torch.as_tensor(_DevView(ptr, shape), device=device)
+
+
+class TiledSolver:
+    """One rank of the row-tiled GAP-TV solver (accelerated GAP, TV prior)."""
+
+    def __init__(self, H, W, C, rank, world, tv_weight=0.1, tv_iter_max=5, _lambda=1.0,
+                 accelerate=True, exchange_every=1, group=None, fused=True):
+        from .engine import Solver
+        self.H, self.W, self.C = H, W, C
+        self.rank, self.world, self.group = rank, world, group
+        self.k = max(1, int(exchange_every))
+        self.halo = self.k * (int(tv_iter_max) - 1)
+        self.lo, self.hi, self.row_lo, self.row_hi = partition_rows(H, world, rank, self.halo)
+        self.local_rows = self.row_hi - self.row_lo
+        self.accelerate = accelerate
+        self.solver = Solver(1, self.local_rows, W, C, method="gap", accelerate=accelerate,
+                             _lambda=_lambda, tv_weight=tv_weight, tv_iter_max=tv_iter_max,
+                             fused=fused)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.exchanges = 0
+
+    # -- data ----------------------------------------------------------------------------
+    def load(self, y_local, Phi_local, x0_local=None, X_orig_local=None):
+        """Inputs restricted to rows [row_lo, row_hi) (device tensors or host arrays)."""
+        self.solver.load(y_local[None], Phi_local,
+                         x0=None if x0_local is None else x0_local[None],
+                         X_orig=None if X_orig_local is None else X_orig_local[None])
+
+    def _fields(self):
+        xp, y1p = self.solver.state_ptrs()
+        f = [_wrap(xp, (self.local_rows, self.W, self.C), self.device)]
+        if self.accelerate:
+            f.append(_wrap(y1p, (self.local_rows, self.W), self.device))
+        return f
+
+    def run(self, iters):
+        done = 0
+        while done < iters:
+            n = min(self.k, iters - done)
+            self.solver.run(n)
+            done += n
+            # always refresh, so that a following run() starts from exact halos
+            exchange_halos(self._fields(), self.H, self.halo, self.rank, self.world, self.group)
+            self.exchanges += 1
+
+    def owned(self, out=None):
+        """Owned rows of the current estimate as a device tensor [hi-lo, W, C]."""
+        x = self._fields()[0]
+        res = x[self.lo - self.row_lo:self.hi - self.row_lo]
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res.clone()
+
+    @property
+    def uses_fused(self):
+        return self.solver.uses_fused
+
+    @property
+    def refined_iters(self):
+        return self.solver.refined_iters
+
+    def close(self):
+        self.solver.close()
+
+    # -- end-to-end measurement used by bench.py -------------------------------------------
+    def e2e_measure(self, y_local, Phi_local, iters, steps):
+        """Host-buffer path at N GPUs: pinned host inputs -> device -> solve -> owned rows back."""
+        import time
+        yh = y_local.cpu().pin_memory()
+        Ph = Phi_local.cpu().pin_memory()
+        out = torch.empty((self.hi - self.lo, self.W, self.C), dtype=torch.float32).pin_memory()
+
+        def step():
+            self.load(yh.cuda(non_blocking=True), Ph.cuda(non_blocking=True))
+            self.run(iters)
+            out.copy_(self.owned(), non_blocking=True)
+            torch.cuda.synchronize()
+        step()
+        if self.world > 1:
+            dist.barrier(self.group)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps)):
+            step()
+        if self.world > 1:
+            dist.barrier(self.group)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX, group=self.group)
+        h2d = torch.tensor([yh.numel() * 4 + Ph.numel() * 4], dtype=torch.float64, device="cuda")
+        d2h = torch.tensor([out.numel() * 4], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(h2d, group=self.group)
+            dist.all_reduce(d2h, group=self.group)
+        return {"value": max(1, steps) * iters / float(dt[0]), "unit": "it/s",
+                "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
+                "steps": max(1, steps), "api": "scipnp.tiled.TiledSolver (pinned host buffers per rank)"}
+
+
+def tiled_reference_run(step_fn, fields, H, halo, k, iters, rank, world, group=None):
+    """Backend-agnostic driver of the tiling protocol, used by the CPU (gloo) tests: ``step_fn``
+    advances the local state by one outer iteration in place; halos are refreshed every k."""
+    done = 0
+    while done < iters:
+        n = min(k, iters - done)
+        for _ in range(n):
+            step_fn()
+        done += n
+        exchange_halos(fields(), H, halo, rank, world, group)
