@@ -159,9 +159,28 @@ int scipnp_solver_load(scipnp_solver *s, const float *y, const float *Phi,
                        const float *Phi_sum, const float *x0, const float *X_orig,
                        void *stream);
 
-/* Run `iters` outer iterations on `stream` (asynchronous).  psnr_all entries are
- * appended to an internal device array read by scipnp_solver_psnr.             */
+/* Run `iters` outer iterations on `stream`.  On the fused path the call returns
+ * after the stream has drained (it has to look at the early-stop flag and, if it
+ * is raised, redoes the run on the exact path); on the exact path it is
+ * asynchronous.  psnr_all entries are appended to an internal device array read
+ * by scipnp_solver_psnr.                                                        */
 int scipnp_solver_run(scipnp_solver *s, int iters, void *stream);
+
+/* The pieces of scipnp_solver_run, for callers that interleave their own work
+ * between iterations (the row-tiled multi-GPU driver refreshes halos):
+ *   _begin       snapshot the state and clear the early-stop flag   (asynchronous)
+ *   _step_async  enqueue `iters` iterations on the current path     (asynchronous)
+ *   _fired       drain the stream; *fired != 0 if the reference would have
+ *                stopped some TV slice early since _begin
+ *   _rollback    restore the snapshot taken by _begin               (asynchronous)
+ *   _set_path    1 = fused kernel, 0 = exact kernels, for the following steps
+ *   _add_refined account iterations the caller redid on the exact path          */
+int scipnp_solver_begin(scipnp_solver *s, void *stream);
+int scipnp_solver_step_async(scipnp_solver *s, int iters, void *stream);
+int scipnp_solver_fired(scipnp_solver *s, int *fired, void *stream);
+int scipnp_solver_rollback(scipnp_solver *s, void *stream);
+int scipnp_solver_set_path(scipnp_solver *s, int fused);
+int scipnp_solver_add_refined(scipnp_solver *s, int iters);
 
 /* Copy the current estimate (GAP: x after TV; ADMM: x before TV, as the
  * reference returns) to a host or device buffer and synchronise the stream.    */

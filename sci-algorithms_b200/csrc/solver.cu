@@ -40,7 +40,8 @@ struct scipnp_solver {
     int* flags = nullptr;      // [1]
     // host state
     bool loaded = false, has_orig = false, use_fused = false;
-    int iters_done = 0, psnr_count = 0, refined = 0;
+    int iters_done = 0, psnr_count = 0, refined = 0, begin_iter = 0;
+    bool fused_possible = false;
     long long launches0 = 0;
     std::vector<void*> owned;
 
@@ -90,6 +91,7 @@ int scipnp_solver_create(const scipnp_params* pp, scipnp_solver** out) {
     s->n_phi = s->n_phisum * p.C;
     const int mode = p.method == 1 ? MODE_ADMM : (p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN);
     s->use_fused = p.fused && fused_supported(mode, p.B, p.H, p.W, p.C, p.tv_iter_max);
+    s->fused_possible = s->use_fused;
     DM(s->xa, s->n_frame, float);
     DM(s->xb, s->n_frame, float);
     DM(s->y, s->n_meas, float);
@@ -218,47 +220,90 @@ static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
     return record_sqerr(s, k, p.method == 0 ? s->xa : s->xproj, st);
 }
 
+// ---- run = begin + step_async + commit; the pieces are public so that a caller that
+//      interleaves its own work between iterations (the row-tiled multi-GPU driver exchanges
+//      halos) can keep everything asynchronous and still get the exact-path guarantee.
+
+int scipnp_solver_begin(scipnp_solver* s, void* stream) {
+    SCIPNP_REQUIRE(s, "null solver");
+    if (!s->loaded) { set_error("scipnp_solver_begin before scipnp_solver_load"); return SCIPNP_ESTATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    s->begin_iter = s->iters_done;
+    if (!s->xsnap) return SCIPNP_OK;          // handle created without the fused path: nothing to roll back
+    SCIPNP_CUDA(cudaMemcpyAsync(s->xsnap, s->xa, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (s->p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1snap, s->y1a, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else SCIPNP_CUDA(cudaMemcpyAsync(s->bsnap, s->ba, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SCIPNP_CUDA(cudaMemsetAsync(s->flags, 0, 4 * sizeof(int), st));
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_step_async(scipnp_solver* s, int iters, void* stream) {
+    SCIPNP_REQUIRE(s, "null solver");
+    SCIPNP_REQUIRE(iters >= 0, "negative iteration count");
+    if (!s->loaded) { set_error("scipnp_solver_step_async before scipnp_solver_load"); return SCIPNP_ESTATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const scipnp_params& p = s->p;
+    if (!s->use_fused)
+        if (int e = ensure_exact_buffers(s)) return e;
+    for (int i = 0; i < iters; ++i)
+        if (int e = s->use_fused ? step_fused(s, s->iters_done + i, st) : step_exact(s, s->iters_done + i, st)) return e;
+    s->iters_done += iters;
+    if (s->has_orig) s->psnr_count = s->iters_done < kPsnrCap / p.B ? s->iters_done : kPsnrCap / p.B;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_fired(scipnp_solver* s, int* fired, void* stream) {
+    SCIPNP_REQUIRE(s && fired, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int flag = 0;
+    if (s->xsnap) SCIPNP_CUDA(cudaMemcpyAsync(&flag, s->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCIPNP_CUDA(cudaStreamSynchronize(st));
+    *fired = flag;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_rollback(scipnp_solver* s, void* stream) {
+    SCIPNP_REQUIRE(s, "null solver");
+    if (!s->xsnap) { set_error("this handle keeps no snapshot (created with fused = 0)"); return SCIPNP_ESTATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const scipnp_params& p = s->p;
+    SCIPNP_CUDA(cudaMemcpyAsync(s->xa, s->xsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1a, s->y1snap, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else SCIPNP_CUDA(cudaMemcpyAsync(s->ba, s->bsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const int k0 = s->begin_iter, capi = kPsnrCap / p.B;
+    const int n = s->iters_done - k0 < capi - k0 ? s->iters_done - k0 : (capi - k0 > 0 ? capi - k0 : 0);
+    if (n > 0) SCIPNP_CUDA(cudaMemsetAsync(s->sqerr + (size_t)k0 * p.B, 0, (size_t)n * p.B * sizeof(double), st));
+    SCIPNP_CUDA(cudaMemsetAsync(s->flags, 0, 4 * sizeof(int), st));
+    s->iters_done = k0;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_set_path(scipnp_solver* s, int fused) {
+    SCIPNP_REQUIRE(s, "null solver");
+    if (fused && !s->fused_possible) { set_error("the fused path does not cover this configuration"); return SCIPNP_ESTATE; }
+    s->use_fused = fused != 0;
+    return SCIPNP_OK;
+}
+
 int scipnp_solver_run(scipnp_solver* s, int iters, void* stream) {
     SCIPNP_REQUIRE(s, "null solver");
     SCIPNP_REQUIRE(iters >= 0, "negative iteration count");
     if (!s->loaded) { set_error("scipnp_solver_run before scipnp_solver_load"); return SCIPNP_ESTATE; }
-    cudaStream_t st = (cudaStream_t)stream;
-    const scipnp_params& p = s->p;
-    const int k0 = s->iters_done;
-    if (!s->use_fused) {
-        if (int e = ensure_exact_buffers(s)) return e;
-        for (int i = 0; i < iters; ++i)
-            if (int e = step_exact(s, k0 + i, st)) return e;
-        s->iters_done += iters;
-        if (s->has_orig) s->psnr_count = s->iters_done < kPsnrCap / p.B ? s->iters_done : kPsnrCap / p.B;
-        return SCIPNP_OK;
-    }
-    // fused path with rollback
-    SCIPNP_CUDA(cudaMemcpyAsync(s->xsnap, s->xa, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1snap, s->y1a, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    else SCIPNP_CUDA(cudaMemcpyAsync(s->bsnap, s->ba, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    SCIPNP_CUDA(cudaMemsetAsync(s->flags, 0, 4 * sizeof(int), st));
-    for (int i = 0; i < iters; ++i)
-        if (int e = step_fused(s, k0 + i, st)) return e;
-    int flag = 0;
-    SCIPNP_CUDA(cudaMemcpyAsync(&flag, s->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SCIPNP_CUDA(cudaStreamSynchronize(st));
-    if (flag) {
+    if (!s->use_fused) return scipnp_solver_step_async(s, iters, stream);
+    if (int e = scipnp_solver_begin(s, stream)) return e;
+    if (int e = scipnp_solver_step_async(s, iters, stream)) return e;
+    int fired = 0;
+    if (int e = scipnp_solver_fired(s, &fired, stream)) return e;
+    if (fired) {
         // the reference would have stopped a TV slice early somewhere in this run:
         // redo the run on the exact path from the snapshot
-        if (int e = ensure_exact_buffers(s)) return e;
-        SCIPNP_CUDA(cudaMemcpyAsync(s->xa, s->xsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        if (p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1a, s->y1snap, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        else SCIPNP_CUDA(cudaMemcpyAsync(s->ba, s->bsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        int capi = kPsnrCap / p.B;
-        int n = iters < capi - k0 ? iters : (capi - k0 > 0 ? capi - k0 : 0);
-        if (n > 0) SCIPNP_CUDA(cudaMemsetAsync(s->sqerr + (size_t)k0 * p.B, 0, (size_t)n * p.B * sizeof(double), st));
-        for (int i = 0; i < iters; ++i)
-            if (int e = step_exact(s, k0 + i, st)) return e;
+        if (int e = scipnp_solver_rollback(s, stream)) return e;
+        s->use_fused = false;
+        int e = scipnp_solver_step_async(s, iters, stream);
+        s->use_fused = true;
+        if (e) return e;
         s->refined += iters;
     }
-    s->iters_done += iters;
-    if (s->has_orig) s->psnr_count = s->iters_done < kPsnrCap / p.B ? s->iters_done : kPsnrCap / p.B;
     return SCIPNP_OK;
 }
 
@@ -293,6 +338,12 @@ int scipnp_solver_psnr(scipnp_solver* s, double* psnr_all, int cap, int* count, 
         double mse = psnr_all[i] / per;
         psnr_all[i] = (mse == 0.0) ? 100.0 : 20.0 * log10(1.0 / sqrt(mse));   // utils.py:32-36
     }
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_add_refined(scipnp_solver* s, int iters) {
+    SCIPNP_REQUIRE(s, "null solver");
+    s->refined += iters;
     return SCIPNP_OK;
 }
 

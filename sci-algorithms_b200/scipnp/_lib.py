@@ -68,6 +68,12 @@ _SIGS = {
     "scipnp_solver_destroy": (C.c_int, [_vp]),
     "scipnp_solver_load": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "scipnp_solver_run": (C.c_int, [_vp, _i, _vp]),
+    "scipnp_solver_begin": (C.c_int, [_vp, _vp]),
+    "scipnp_solver_step_async": (C.c_int, [_vp, _i, _vp]),
+    "scipnp_solver_fired": (C.c_int, [_vp, C.POINTER(_i), _vp]),
+    "scipnp_solver_rollback": (C.c_int, [_vp, _vp]),
+    "scipnp_solver_set_path": (C.c_int, [_vp, _i]),
+    "scipnp_solver_add_refined": (C.c_int, [_vp, _i]),
     "scipnp_solver_get_x": (C.c_int, [_vp, _fp, _vp]),
     "scipnp_solver_psnr": (C.c_int, [_vp, C.POINTER(C.c_double), _i, C.POINTER(_i), _vp]),
     "scipnp_solver_sqerr": (C.c_int, [_vp, C.POINTER(C.c_double), _i, C.POINTER(_i), _vp]),

@@ -130,6 +130,27 @@ class Solver:
     def run(self, iters):
         check(lib.scipnp_solver_run(self._h, int(iters), stream_ptr()))
 
+    # pieces of run() for callers that interleave their own work (see include/scipnp.h)
+    def begin(self):
+        check(lib.scipnp_solver_begin(self._h, stream_ptr()))
+
+    def step_async(self, iters):
+        check(lib.scipnp_solver_step_async(self._h, int(iters), stream_ptr()))
+
+    def fired(self):
+        f = ct.c_int(0)
+        check(lib.scipnp_solver_fired(self._h, ct.byref(f), stream_ptr()))
+        return bool(f.value)
+
+    def rollback(self):
+        check(lib.scipnp_solver_rollback(self._h, stream_ptr()))
+
+    def set_path(self, fused):
+        check(lib.scipnp_solver_set_path(self._h, 1 if fused else 0))
+
+    def add_refined(self, iters):
+        check(lib.scipnp_solver_add_refined(self._h, int(iters)))
+
     def get_x(self, out=None):
         """Current estimate as NumPy (default) or into a given tensor/array."""
         if out is None:

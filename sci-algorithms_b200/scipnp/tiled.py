@@ -121,15 +121,37 @@ class TiledSolver:
             f.append(_wrap(y1p, (self.local_rows, self.W), self.device))
         return f
 
-    def run(self, iters):
+    def _sweep(self, iters):
         done = 0
         while done < iters:
             n = min(self.k, iters - done)
-            self.solver.run(n)
+            self.solver.step_async(n)
             done += n
             # always refresh, so that a following run() starts from exact halos
             exchange_halos(self._fields(), self.H, self.halo, self.rank, self.world, self.group)
             self.exchanges += 1
+
+    def run(self, iters):
+        """`iters` outer iterations, everything enqueued asynchronously; one host sync at the
+        end to agree (over all ranks) on whether the TV early stop fired anywhere, in which
+        case every rank rolls back and redoes the run on the exact path."""
+        fused = self.solver.uses_fused
+        if fused:
+            self.solver.begin()
+        self._sweep(iters)
+        if not fused:
+            return
+        flag = torch.tensor([1 if self.solver.fired() else 0], dtype=torch.int32, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()):
+            self.solver.rollback()
+            self.solver.set_path(False)
+            try:
+                self._sweep(iters)
+            finally:
+                self.solver.set_path(True)
+            self.solver.add_refined(iters)
 
     def owned(self, out=None):
         """Owned rows of the current estimate as a device tensor [hi-lo, W, C]."""
