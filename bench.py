@@ -300,7 +300,7 @@ def run_ours(args):
     cpu_val, cpu_wall = (None, None)
     cpu = None
     if world == 1 and not args.no_cpu:
-        rows, cit = 192, 6
+        rows, cit = 192, 12
         cpu_val, cpu_wall = cpu_baseline(rows, cit, 1)
         cpu = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "%d-row x %d x %d band of the scene, %d outer iterations, %.1f s of NumPy "
