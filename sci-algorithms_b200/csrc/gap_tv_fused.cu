@@ -147,19 +147,11 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     const int own = 32 - 2 * R;
     fp.ngroups = (a.W + own - 1) / own;
     const int gx = (fp.ngroups + fp.NG - 1) / fp.NG;
-    // row segments: enough CTAs for ~4 waves of 2 CTAs/SM, but segments of >= 32 rows
-    const long long target = 8LL * num_sms();
-    long long nseg = (target + (long long)gx * a.B - 1) / ((long long)gx * a.B);
-    long long max_seg = (a.H + 31) / 32;
-    if (nseg > max_seg) nseg = max_seg;
-    if (nseg < 1) nseg = 1;
-    fp.seg_rows = (int)((a.H + nseg - 1) / nseg);
-    nseg = (a.H + fp.seg_rows - 1) / fp.seg_rows;
+    fp.seg_rows = a.H;          // the launcher picks the row segmentation (occupancy-aware)
     fp.phi_bstride = a.phi_batched ? (long long)a.H * a.W * a.C : 0;
     fp.ps_bstride = a.phi_batched ? (long long)a.H * a.W : 0;
     fp.phi_batched = a.phi_batched ? 1 : 0;
-    if (nseg > 65535) { set_error("too many row segments"); return SCIPNP_EINVAL; }
-    dim3 grid(gx, (unsigned)nseg, a.B);
+    dim3 grid(gx, 1, a.B);
 
     // TMA descriptors of this launch (x ping-pongs, so they are rebuilt per call: ~1 us each on the host)
     alignas(64) FusedMaps maps;

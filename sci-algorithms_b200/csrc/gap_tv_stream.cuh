@@ -437,10 +437,34 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
 template <int R> int launch_stream_r(int mode, int K, const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st);
 
 template <int R, int MODE, int K>
-int launch_stream_k(const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st) {
+int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream_t st) {
     auto kfn = gap_tv_stream_kernel<R, MODE, true, K>;
     constexpr Smem L = smem_layout(K, fused_groups(K));
-    SCIPNP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    static int ctas_per_sm = 0;            // resident CTAs of this instance, queried once
+    if (!ctas_per_sm) {
+        SCIPNP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        int n = 0;
+        SCIPNP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, fused_threads(K), L.total));
+        ctas_per_sm = n > 0 ? n : 1;
+    }
+    // Row segments.  Cost model: waves * (rows per segment + warm-up/drain rows); the grid is
+    // (pixel-group bundles) x (segments) x (batch), all CTAs equal, so a partial last wave is
+    // pure loss.  Segments shorter than 32 rows are not considered.
+    const long long slots = (long long)ctas_per_sm * num_sms();
+    const long long per_seg = (long long)grid.x * grid.z;
+    const int H = fp.H, max_seg = (H + 31) / 32;
+    long long best_cost = -1;
+    int best = 1;
+    for (int nseg = 1; nseg <= max_seg && nseg <= 65535; ++nseg) {
+        const int rows = (H + nseg - 1) / nseg;
+        const int n2 = (H + rows - 1) / rows;
+        if (n2 != nseg) continue;
+        const long long waves = (per_seg * nseg + slots - 1) / slots;
+        const long long cost = waves * (rows + 2 * R + RB);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nseg; }
+    }
+    fp.seg_rows = (H + best - 1) / best;
+    grid.y = (unsigned)((H + fp.seg_rows - 1) / fp.seg_rows);
     kfn<<<grid, fused_threads(K), L.total, st>>>(fp, maps);
     return SCIPNP_OK;
 }
