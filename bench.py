@@ -203,7 +203,7 @@ def run_ours(args):
     if world > 1:
         from scipnp.tiled import TiledSolver
         solver = TiledSolver(H, W, CR, rank, world, tv_weight=TV_WEIGHT, tv_iter_max=TV_ITER,
-                             exchange_every=args.exchange_every)
+                             exchange_every=args.exchange_every, transport=args.transport)
         y, Phi, _ = device_scene(torch, solver.local_rows, W, CR, row0=solver.row_lo)
         load = lambda: solver.load(y, Phi)
     else:
@@ -315,7 +315,8 @@ def run_ours(args):
                    "l2": "state per iteration (2.5 GB) exceeds the 126 MB L2; no flush needed",
                    "path": "fused" if fused else "exact", "refined_iters": refined,
                    "parallelism": ("row-tiled x%d, %d halo rows, neighbour exchange every %d iteration(s)"
-                                   % (world, 4 * args.exchange_every, args.exchange_every)) if world > 1 else "single GPU"},
+                                   % (world, 4 * args.exchange_every, args.exchange_every)) if world > 1 else "single GPU",
+                   "halo_transport": getattr(solver, "transport", None) if world > 1 else None},
         "gpixel_frames_per_s": value * H * W * CR / 1e9,
         "ms_per_iteration": iter_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -348,6 +349,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange-every", type=int, default=2,
                     help="N > 1: outer iterations between halo exchanges (halo = 4x that many rows)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: halo transport (p2p = CUDA-IPC peer pulls, nccl = send/recv)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -204,6 +204,30 @@ long long scipnp_solver_launch_count(scipnp_solver *s);
 /* 1 when the handle runs the one-pass fused iteration, 0 on the exact path.    */
 int scipnp_solver_uses_fused(scipnp_solver *s);
 
+/* --------------------------------------------------------------------------
+ * Row-tiled multi-GPU mode (one process per GPU on one node; no counterpart in
+ * the single-process reference).  The handle holds rows [row_lo, row_hi) of a
+ * taller scene (so p.H = row_hi - row_lo, B = 1, GAP) and owns [lo, hi); the
+ * other rows are halo copies of rows owned by the neighbouring ranks.  The
+ * neighbours' buffers are mapped with CUDA IPC; an exchange pulls the halo rows
+ * of x and y1 straight over NVLink, ordered by flags the ranks write into each
+ * other's memory (no host round trip, no collective):
+ *   _tiling        declare the row ranges of this rank
+ *   _ipc_export    blob (scipnp_solver_ipc_blob_bytes() bytes) describing my buffers
+ *   _ipc_attach    map a neighbour's blob; side 0 = rank above, 1 = rank below;
+ *                  peer_row_lo = global row of that rank's local row 0
+ *   _exchange      enqueue one halo refresh on `stream`
+ *   _run_tiled     `iters` iterations, an exchange every `k` and after the last
+ *   _sync_error    drains the stream; *timed_out != 0 if a neighbour never showed up
+ * -------------------------------------------------------------------------- */
+int scipnp_solver_ipc_blob_bytes(void);
+int scipnp_solver_tiling(scipnp_solver *s, int lo, int hi, int row_lo, int row_hi);
+int scipnp_solver_ipc_export(scipnp_solver *s, unsigned char *blob);
+int scipnp_solver_ipc_attach(scipnp_solver *s, int side, const unsigned char *blob, int peer_row_lo);
+int scipnp_solver_exchange(scipnp_solver *s, void *stream);
+int scipnp_solver_run_tiled(scipnp_solver *s, int iters, int k, void *stream);
+int scipnp_solver_sync_error(scipnp_solver *s, int *timed_out, void *stream);
+
 /* Host-buffer one-call entries (what a ctypes / cffi binding of the reference
  * would call in place of gap_denoise / admm_denoise).  Synchronous.  psnr_all
  * must hold iters*B doubles when X_orig is given (may be NULL otherwise).      */

@@ -44,6 +44,23 @@ struct scipnp_solver {
     bool fused_possible = false;
     long long launches0 = 0;
     std::vector<void*> owned;
+    // ---- row-tiled multi-GPU mode: direct peer access to the neighbours' buffers ----
+    struct PeerLink {
+        bool present = false;
+        float* x[2] = {nullptr, nullptr};     // the neighbour's two x buffers (IPC-mapped)
+        float* y1[2] = {nullptr, nullptr};
+        int* sync = nullptr;                  // the neighbour's flag block
+        int row_lo = 0;                       // global row of the neighbour's local row 0
+        void* mapped[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    };
+    bool tiled = false;
+    int t_lo = 0, t_hi = 0, t_row_lo = 0, t_row_hi = 0;
+    float* xbuf[2] = {nullptr, nullptr};      // identity of my own two x / y1 buffers
+    float* y1buf[2] = {nullptr, nullptr};
+    int* sync = nullptr;                      // [0] ready<-up [1] ready<-down [2] ack<-up [3] ack<-down [4] timeout
+    int epoch = 0;
+    bool ack_pending = false;
+    PeerLink up, dn;
 
     float* x_cur() { return xa; }
 };
@@ -66,6 +83,9 @@ extern "C" {
 
 int scipnp_solver_destroy(scipnp_solver* s) {
     if (!s) return SCIPNP_OK;
+    for (scipnp_solver::PeerLink* l : {&s->up, &s->dn})
+        for (void* m : l->mapped)
+            if (m) cudaIpcCloseMemHandle(m);
     for (void* p : s->owned) cudaFree(p);
     delete s;
     return SCIPNP_OK;
@@ -116,6 +136,8 @@ int scipnp_solver_create(const scipnp_params* pp, scipnp_solver** out) {
         s->fws_bytes = fused_workspace_bytes(p.B, p.H, p.W, p.C, p.tv_iter_max);
         DM(s->fws, s->fws_bytes, char);
     }
+    s->xbuf[0] = s->xa; s->xbuf[1] = s->xb;
+    s->y1buf[0] = s->y1a; s->y1buf[1] = s->y1b;
     // exact-path workspace is allocated lazily (only the exact path or a rollback needs it)
     s->launches0 = g_launches;
     *out = s;
@@ -363,6 +385,170 @@ int scipnp_solver_state(scipnp_solver* s, float** x_cur, float** y1_cur) {
 int scipnp_solver_uses_fused(scipnp_solver* s) { return s && s->use_fused ? 1 : 0; }
 
 long long scipnp_solver_launch_count(scipnp_solver* s) { return s ? g_launches - s->launches0 : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Row-tiled multi-GPU mode ("single UHD scene"): this handle holds rows
+// [row_lo, row_hi) of a taller scene and owns [lo, hi); the rows in between are halo copies of the
+// neighbours' owned rows.  Neighbours are other processes on the same node: their buffers are
+// mapped with CUDA IPC and the halo rows are pulled straight over NVLink, ordered by flags that
+// the ranks write into each other's memory.  No host round trip and no collective per exchange.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void tile_signal_kernel(int* a, int* b, int value) {
+    __threadfence_system();
+    if (a) *reinterpret_cast<volatile int*>(a) = value;
+    if (b) *reinterpret_cast<volatile int*>(b) = value;
+    __threadfence_system();
+}
+
+// spin (with back-off) until both flags reached `need`; gives up after ~8 s and raises sync[4]
+__global__ void tile_wait_kernel(volatile int* f0, volatile int* f1, int need, int* timeout_flag) {
+    const long long t0 = clock64();
+    while ((f0 && *f0 < need) || (f1 && *f1 < need)) {
+        __nanosleep(200);
+        if (clock64() - t0 > 16000000000LL) { atomicExch(timeout_flag, 1); break; }
+    }
+    __threadfence_system();
+}
+
+constexpr int kIpcBlob = 5 * 64;
+
+}  // namespace
+
+int scipnp_solver_ipc_blob_bytes(void) { return kIpcBlob; }
+
+int scipnp_solver_tiling(scipnp_solver* s, int lo, int hi, int row_lo, int row_hi) {
+    SCIPNP_REQUIRE(s, "null solver");
+    SCIPNP_REQUIRE(s->p.B == 1 && s->p.method == 0, "tiling covers a single GAP scene (B = 1)");
+    SCIPNP_REQUIRE(row_lo <= lo && lo < hi && hi <= row_hi && row_hi - row_lo == s->p.H, "inconsistent row ranges");
+    s->t_lo = lo; s->t_hi = hi; s->t_row_lo = row_lo; s->t_row_hi = row_hi;
+    if (!s->sync) {
+        if (int e = dmalloc(s, (void**)&s->sync, 8 * sizeof(int))) return e;
+        SCIPNP_CUDA(cudaMemset(s->sync, 0, 8 * sizeof(int)));
+    }
+    s->tiled = true;
+    s->epoch = 0;
+    s->ack_pending = false;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_ipc_export(scipnp_solver* s, unsigned char* blob) {
+    SCIPNP_REQUIRE(s && blob, "null pointer");
+    if (!s->tiled) { set_error("call scipnp_solver_tiling first"); return SCIPNP_ESTATE; }
+    memset(blob, 0, kIpcBlob);
+    void* ptrs[5] = {s->xbuf[0], s->xbuf[1], s->y1buf[0], s->y1buf[1], s->sync};
+    for (int i = 0; i < 5; ++i) {
+        if (!ptrs[i]) continue;
+        cudaIpcMemHandle_t h;
+        SCIPNP_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
+        static_assert(sizeof(h) == 64, "unexpected IPC handle size");
+        memcpy(blob + 64 * i, &h, 64);
+    }
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_ipc_attach(scipnp_solver* s, int side, const unsigned char* blob, int peer_row_lo) {
+    SCIPNP_REQUIRE(s && blob, "null pointer");
+    SCIPNP_REQUIRE(side == 0 || side == 1, "side must be 0 (up) or 1 (down)");
+    if (!s->tiled) { set_error("call scipnp_solver_tiling first"); return SCIPNP_ESTATE; }
+    scipnp_solver::PeerLink& l = side == 0 ? s->up : s->dn;
+    static const unsigned char zero[64] = {0};
+    for (int i = 0; i < 5; ++i) {
+        if (!memcmp(blob + 64 * i, zero, 64)) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, blob + 64 * i, 64);
+        SCIPNP_CUDA(cudaIpcOpenMemHandle(&l.mapped[i], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    l.x[0] = (float*)l.mapped[0]; l.x[1] = (float*)l.mapped[1];
+    l.y1[0] = (float*)l.mapped[2]; l.y1[1] = (float*)l.mapped[3];
+    l.sync = (int*)l.mapped[4];
+    l.row_lo = peer_row_lo;
+    SCIPNP_REQUIRE(l.x[0] && l.x[1] && l.sync, "incomplete IPC blob");
+    l.present = true;
+    return SCIPNP_OK;
+}
+
+// wait until both neighbours have finished reading my buffers for the last exchange
+static int tile_wait_ack(scipnp_solver* s, cudaStream_t st) {
+    if (!s->ack_pending) return SCIPNP_OK;
+    tile_wait_kernel<<<1, 1, 0, st>>>(s->up.present ? s->sync + 2 : nullptr, s->dn.present ? s->sync + 3 : nullptr,
+                                     s->epoch, s->sync + 4);
+    count_launch();
+    s->ack_pending = false;
+    return check_launch("tile_wait_kernel");
+}
+
+int scipnp_solver_exchange(scipnp_solver* s, void* stream) {
+    SCIPNP_REQUIRE(s, "null solver");
+    if (!s->tiled) { set_error("not a tiled solver"); return SCIPNP_ESTATE; }
+    if (!s->up.present && !s->dn.present) return SCIPNP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int e = tile_wait_ack(s, st)) return e;
+    const int e = ++s->epoch;
+    const int W = s->p.W, C = s->p.C;
+    const int xi = s->xa == s->xbuf[0] ? 0 : 1;
+    const int yi = s->y1a == s->y1buf[0] ? 0 : 1;
+    // 1. my rows of this epoch are final: tell the neighbours (I am the upper one's "down" side)
+    tile_signal_kernel<<<1, 1, 0, st>>>(s->up.present ? s->up.sync + 1 : nullptr,
+                                       s->dn.present ? s->dn.sync + 0 : nullptr, e);
+    // 2. wait for theirs
+    tile_wait_kernel<<<1, 1, 0, st>>>(s->up.present ? s->sync + 0 : nullptr, s->dn.present ? s->sync + 1 : nullptr,
+                                     e, s->sync + 4);
+    count_launch(2);
+    // 3. pull my halo rows out of the neighbours' owned rows
+    const size_t rowx = (size_t)W * C, rowy = (size_t)W;
+    if (s->up.present) {
+        const int n = s->t_lo - s->t_row_lo, src = s->t_row_lo - s->up.row_lo;
+        if (n > 0) {
+            SCIPNP_CUDA(cudaMemcpyAsync(s->xa, s->up.x[xi] + src * rowx, n * rowx * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (s->p.accelerate && s->up.y1[yi])
+                SCIPNP_CUDA(cudaMemcpyAsync(s->y1a, s->up.y1[yi] + src * rowy, n * rowy * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (s->dn.present) {
+        const int n = s->t_row_hi - s->t_hi, dst = s->t_hi - s->t_row_lo, src = s->t_hi - s->dn.row_lo;
+        if (n > 0) {
+            SCIPNP_CUDA(cudaMemcpyAsync(s->xa + dst * rowx, s->dn.x[xi] + src * rowx, n * rowx * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (s->p.accelerate && s->dn.y1[yi])
+                SCIPNP_CUDA(cudaMemcpyAsync(s->y1a + dst * rowy, s->dn.y1[yi] + src * rowy, n * rowy * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    // 4. acknowledge: the neighbours may overwrite those buffers once they have seen this
+    tile_signal_kernel<<<1, 1, 0, st>>>(s->up.present ? s->up.sync + 3 : nullptr,
+                                       s->dn.present ? s->dn.sync + 2 : nullptr, e);
+    count_launch();
+    s->ack_pending = true;
+    return check_launch("tile exchange");
+}
+
+// `iters` iterations with a halo exchange every `k` (and after the last one); asynchronous
+int scipnp_solver_run_tiled(scipnp_solver* s, int iters, int k, void* stream) {
+    SCIPNP_REQUIRE(s, "null solver");
+    SCIPNP_REQUIRE(iters >= 0 && k >= 1, "bad iteration counts");
+    if (!s->tiled) { set_error("not a tiled solver"); return SCIPNP_ESTATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int it = 0; it < iters; ++it) {
+        // the step after next overwrites the buffer the neighbours pulled from: by the second
+        // step after an exchange their acknowledgement must be in
+        if (s->ack_pending && k > 1 && (it % k) == 1)
+            if (int e = tile_wait_ack(s, st)) return e;
+        if (int e = scipnp_solver_step_async(s, 1, stream)) return e;
+        if ((it + 1) % k == 0 || it + 1 == iters)
+            if (int e = scipnp_solver_exchange(s, stream)) return e;
+    }
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_sync_error(scipnp_solver* s, int* timed_out, void* stream) {
+    SCIPNP_REQUIRE(s && timed_out, "null pointer");
+    *timed_out = 0;
+    if (!s->sync) return SCIPNP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    SCIPNP_CUDA(cudaMemcpyAsync(timed_out, s->sync + 4, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCIPNP_CUDA(cudaStreamSynchronize(st));
+    return SCIPNP_OK;
+}
 
 static int denoise_host(int method, const float* y, const float* Phi, const float* x0,
                         const float* X_orig, const scipnp_params* p, int iters, float* x_out,

@@ -74,6 +74,13 @@ _SIGS = {
     "scipnp_solver_rollback": (C.c_int, [_vp, _vp]),
     "scipnp_solver_set_path": (C.c_int, [_vp, _i]),
     "scipnp_solver_add_refined": (C.c_int, [_vp, _i]),
+    "scipnp_solver_ipc_blob_bytes": (C.c_int, []),
+    "scipnp_solver_tiling": (C.c_int, [_vp, _i, _i, _i, _i]),
+    "scipnp_solver_ipc_export": (C.c_int, [_vp, C.c_char_p]),
+    "scipnp_solver_ipc_attach": (C.c_int, [_vp, _i, C.c_char_p, _i]),
+    "scipnp_solver_exchange": (C.c_int, [_vp, _vp]),
+    "scipnp_solver_run_tiled": (C.c_int, [_vp, _i, _i, _vp]),
+    "scipnp_solver_sync_error": (C.c_int, [_vp, C.POINTER(_i), _vp]),
     "scipnp_solver_get_x": (C.c_int, [_vp, _fp, _vp]),
     "scipnp_solver_psnr": (C.c_int, [_vp, C.POINTER(C.c_double), _i, C.POINTER(_i), _vp]),
     "scipnp_solver_sqerr": (C.c_int, [_vp, C.POINTER(C.c_double), _i, C.POINTER(_i), _vp]),

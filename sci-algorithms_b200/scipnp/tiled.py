@@ -92,7 +92,10 @@ class TiledSolver:
     """One rank of the row-tiled GAP-TV solver (accelerated GAP, TV prior)."""
 
     def __init__(self, H, W, C, rank, world, tv_weight=0.1, tv_iter_max=5, _lambda=1.0,
-                 accelerate=True, exchange_every=1, group=None, fused=True):
+                 accelerate=True, exchange_every=1, group=None, fused=True, transport="nccl"):
+        """transport: "nccl" (send/recv pairs through torch.distributed), "p2p" (CUDA-IPC
+        mapped neighbour buffers, halo rows pulled over NVLink by the library, device-side
+        flags) or "auto" (p2p when every rank can set it up, else nccl)."""
         from .engine import Solver
         self.H, self.W, self.C = H, W, C
         self.rank, self.world, self.group = rank, world, group
@@ -106,6 +109,45 @@ class TiledSolver:
                              fused=fused)
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.exchanges = 0
+        self.transport = "nccl"
+        if transport in ("p2p", "auto") and world > 1:
+            self._setup_p2p(required=(transport == "p2p"))
+
+    def _setup_p2p(self, required):
+        """Map the neighbours' solver buffers (CUDA IPC) so that halo rows are pulled straight
+        over NVLink by the library, with device-side flags instead of NCCL calls.  Needs every
+        halo to lie inside the direct neighbour's owned rows."""
+        import ctypes as ct
+        from ._lib import lib, check
+        plan = _plan(self.H, self.world, self.halo)
+        ok = all(p[1] - p[0] >= self.halo for p in plan)
+        err = None
+        blob = b""
+        try:
+            if ok:
+                check(lib.scipnp_solver_tiling(self.solver._h, self.lo, self.hi, self.row_lo, self.row_hi))
+                n = lib.scipnp_solver_ipc_blob_bytes()
+                buf = ct.create_string_buffer(n)
+                check(lib.scipnp_solver_ipc_export(self.solver._h, buf))
+                blob = buf.raw
+        except Exception as e:      # noqa: BLE001
+            err = e
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, (blob, self.row_lo, err is None and ok), group=self.group)
+        good = all(b[2] for b in blobs)
+        if good:
+            try:
+                for side, other in ((0, self.rank - 1), (1, self.rank + 1)):
+                    if 0 <= other < self.world:
+                        check(lib.scipnp_solver_ipc_attach(self.solver._h, side, blobs[other][0], blobs[other][1]))
+            except Exception as e:      # noqa: BLE001
+                err, good = e, False
+        flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()):
+            self.transport = "p2p"
+        elif required:
+            raise RuntimeError("peer-to-peer halo transport unavailable: %s" % (err or "halo wider than a block"))
 
     # -- data ----------------------------------------------------------------------------
     def load(self, y_local, Phi_local, x0_local=None, X_orig_local=None):
@@ -122,6 +164,12 @@ class TiledSolver:
         return f
 
     def _sweep(self, iters):
+        if self.transport == "p2p":
+            from ._lib import lib, check
+            from .engine import stream_ptr
+            check(lib.scipnp_solver_run_tiled(self.solver._h, int(iters), self.k, stream_ptr()))
+            self.exchanges += (iters + self.k - 1) // self.k
+            return
         done = 0
         while done < iters:
             n = min(self.k, iters - done)
@@ -139,6 +187,8 @@ class TiledSolver:
         if fused:
             self.solver.begin()
         self._sweep(iters)
+        if self.transport == "p2p":
+            self._check_sync()
         if not fused:
             return
         flag = torch.tensor([1 if self.solver.fired() else 0], dtype=torch.int32, device=self.device)
@@ -152,6 +202,15 @@ class TiledSolver:
             finally:
                 self.solver.set_path(True)
             self.solver.add_refined(iters)
+
+    def _check_sync(self):
+        import ctypes as ct
+        from ._lib import lib, check
+        from .engine import stream_ptr
+        t = ct.c_int(0)
+        check(lib.scipnp_solver_sync_error(self.solver._h, ct.byref(t), stream_ptr()))
+        if t.value:
+            raise RuntimeError("rank %d: a neighbour never signalled its halo rows (timeout)" % self.rank)
 
     def owned(self, out=None):
         """Owned rows of the current estimate as a device tensor [hi-lo, W, C]."""
