@@ -147,7 +147,7 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     const int own = 32 - 2 * R;
     fp.ngroups = (a.W + own - 1) / own;
     const int gx = (fp.ngroups + fp.NG - 1) / fp.NG;
-    fp.seg_rows = a.H;          // the launcher picks the row segmentation (occupancy-aware)
+    fp.B = a.B;
     fp.phi_bstride = a.phi_batched ? (long long)a.H * a.W * a.C : 0;
     fp.ps_bstride = a.phi_batched ? (long long)a.H * a.W : 0;
     fp.phi_batched = a.phi_batched ? 1 : 0;

@@ -19,8 +19,7 @@ struct FusedParams {
     const float* y; const float* Phi; const float* Phi_sum;
     double* energy;               // [B][C][R] partial sums of d^2 + w*|g|
     float lambda, tv_c, tv_w;     // tv_c = tau / weight
-    int H, W, C, K, NG, ngroups;  // K = C/4 chunk-warps per pixel group, NG groups per CTA
-    int seg_rows;
+    int B, H, W, C, K, NG, ngroups;  // K = C/4 chunk-warps per pixel group, NG groups per CTA
     int small_tma;                // y / y1 / Phi_sum rows staged by TMA (needs W % 4 == 0), else cp.async
     int phi_batched;
     long long phi_bstride, ps_bstride;   // batch strides (0 when shared)
@@ -215,16 +214,40 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int gi = warp / K, k = warp - gi * K;
-    const int b = blockIdx.z;
-    const int group0 = blockIdx.x * NG;          // first pixel group of this CTA
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t bar_base = smem_base + L.bar_off;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NSLOT; ++i) mbar_init(bar_base + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---- balanced work split: the scene is (batch x pixel-group bundles) column strips of H rows;
+    //      laid end to end they form `total` row units, and every CTA takes the same number of
+    //      consecutive units, i.e. at most a few row segments of neighbouring strips.  No wave
+    //      quantisation, and the warm-up rows of a segment are paid once or twice per CTA.
+    const int nbundles = (p.ngroups + NG - 1) / NG;
+    const long long total = (long long)p.B * nbundles * H;
+    const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
+    long long unit = (long long)blockIdx.x * per_cta;
+    const long long unit_end = min(total, unit + per_cta);
+    int gb = 0;                                  // running block counter: ring slot and mbarrier phase
+#pragma unroll 1
+    while (unit < unit_end) {
+    const int strip = (int)(unit / H);
+    const int r0 = (int)(unit - (long long)strip * H);
+    const int r1 = (int)min((long long)H, r0 + (unit_end - unit));
+    unit += r1 - r0;
+    const int b = strip / nbundles;
+    const int group0 = (strip - b * nbundles) * NG;      // first pixel group of this segment
     const int grp = group0 + gi;
     const bool grp_live = grp < p.ngroups;
     const int px = grp * OWN - R + lane;         // this lane's pixel column
     const bool px_in = grp_live && px >= 0 && px < W;
     const bool own_px = px_in && lane >= R && lane < 32 - R;
 
-    const int r0 = blockIdx.y * p.seg_rows;
-    const int r1 = min(H, r0 + p.seg_rows);
     const int rs = max(0, r0 - R), rend = r1 + R;       // steps rho in [rs, rend)
     const int load_end = min(H, rend);
     const int nblk = (rend - rs + RB - 1) / RB;
@@ -233,13 +256,11 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
 
     const size_t frame_b = (size_t)b * H * W * C;        // batch offsets
     const size_t meas_b = (size_t)b * H * W;
-    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
     // ---- producer: thread 0 programs the TMA unit, RB rows per block ------------------------------
     //      2*NG*K boxes of x / Phi (+ 3*NG rows of y, y1, Phi_sum) land in slot blk % 3 and
     //      complete on that slot's mbarrier.  Pixels left/right of the image are zero-filled by
     //      the TMA unit; rows past the segment are loaded but never used.
-    const uint32_t bar_base = smem_base + L.bar_off;
     constexpr uint32_t kTileTx = 2u * NG * K * BOX_BYTES;
     constexpr uint32_t kSmallTx = (MODE == MODE_GAP_ACC ? 3u : 2u) * NG * RB * 32 * 4;
     const int rowc0 = b * H;                              // row coordinate of the batch element
@@ -248,7 +269,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     constexpr int NSMALL = (3 * NG * RB * 32 + NT - 1) / NT;
     auto issue = [&](int blk) {
         if (blk < nblk) {
-            const int slot = blk % NSLOT;
+            const int slot = (gb + blk) % NSLOT;
             const uint32_t dst = smem_base + slot * L.buf_bytes;
             const int row0 = rs + blk * RB;
             if (tid == 0) {
@@ -294,13 +315,13 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         if (!p.small_tma) cp_async_commit();
     };
     auto wait_block = [&](int blk) {       // tiles (and TMA-staged rows) of block blk have landed
-        if (blk < nblk) mbar_wait(bar_base + (blk % NSLOT) * 8, (blk / NSLOT) & 1);
+        if (blk < nblk) mbar_wait(bar_base + ((gb + blk) % NSLOT) * 8, ((gb + blk) / NSLOT) & 1);
     };
     // partial dot products of this warp's chunk for the rows of block `blk`
     auto phase_a = [&](int blk) {
         if (blk >= nblk) return;
-        const unsigned char* buf = smem_raw + (blk % NSLOT) * L.buf_bytes;
-        float* part = reinterpret_cast<float*>(smem_raw + L.part_off + (blk & 1) * L.part_bytes);
+        const unsigned char* buf = smem_raw + ((gb + blk) % NSLOT) * L.buf_bytes;
+        float* part = reinterpret_cast<float*>(smem_raw + L.part_off + ((gb + blk) & 1) * L.part_bytes);
         float4 xv[RB], pv[RB];
 #pragma unroll
         for (int j = 0; j < RB; ++j) {           // all loads first: one shared-memory round trip
@@ -373,13 +394,6 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
             *reinterpret_cast<float4*>(xo + ((size_t)orow * W + px) * C + 4 * k) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
 
-    if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < NSLOT; ++i) mbar_init(bar_base + i * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    }
-    __syncthreads();
     issue(0);
     issue(1);
     wait_block(0);
@@ -393,8 +407,8 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         issue(blk + 2);
         wait_block(blk + 1);
         phase_a(blk + 1);
-        const unsigned char* buf = smem_raw + (blk % NSLOT) * L.buf_bytes;
-        const float* part = reinterpret_cast<const float*>(smem_raw + L.part_off + (blk & 1) * L.part_bytes);
+        const unsigned char* buf = smem_raw + ((gb + blk) % NSLOT) * L.buf_bytes;
+        const float* part = reinterpret_cast<const float*>(smem_raw + L.part_off + ((gb + blk) & 1) * L.part_bytes);
         const int rho0 = rs + blk * RB;
         if (rho0 >= fast_lo && rho0 + RB - 1 <= fast_hi) {
 #pragma unroll
@@ -431,6 +445,11 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
                 if (lane == 0 && grp_live) atomicAdd(p.energy + ((size_t)b * C + 4 * k + ch) * R + i, (double)v);
             }
     }
+    // segment boundary: every warp is done with the staging ring and the partial sums
+    gb += nblk;
+    if (!p.small_tma) cp_async_wait<0>();
+    __syncthreads();
+    }   // while (unit < unit_end)
 }
 
 // one launcher per R, defined in fused_inst_r{2,3,4}.cu
@@ -447,24 +466,15 @@ int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream
         SCIPNP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, fused_threads(K), L.total));
         ctas_per_sm = n > 0 ? n : 1;
     }
-    // Row segments.  Cost model: waves * (rows per segment + warm-up/drain rows); the grid is
-    // (pixel-group bundles) x (segments) x (batch), all CTAs equal, so a partial last wave is
-    // pure loss.  Segments shorter than 32 rows are not considered.
+    // One resident wave: every CTA takes an equal share of the (batch x bundle x row) units
+    // (see the kernel), but not less than 32 rows so that warm-up rows stay a small fraction.
     const long long slots = (long long)ctas_per_sm * num_sms();
-    const long long per_seg = (long long)grid.x * grid.z;
-    const int H = fp.H, max_seg = (H + 31) / 32;
-    long long best_cost = -1;
-    int best = 1;
-    for (int nseg = 1; nseg <= max_seg && nseg <= 65535; ++nseg) {
-        const int rows = (H + nseg - 1) / nseg;
-        const int n2 = (H + rows - 1) / rows;
-        if (n2 != nseg) continue;
-        const long long waves = (per_seg * nseg + slots - 1) / slots;
-        const long long cost = waves * (rows + 2 * R + RB);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = nseg; }
-    }
-    fp.seg_rows = (H + best - 1) / best;
-    grid.y = (unsigned)((H + fp.seg_rows - 1) / fp.seg_rows);
+    const long long nbundles = (fp.ngroups + fused_groups(K) - 1) / fused_groups(K);
+    const long long total = (long long)fp.B * nbundles * fp.H;
+    long long n = total / 32;
+    if (n > slots) n = slots;
+    if (n < 1) n = 1;
+    grid = dim3((unsigned)n, 1, 1);
     kfn<<<grid, fused_threads(K), L.total, st>>>(fp, maps);
     return SCIPNP_OK;
 }
