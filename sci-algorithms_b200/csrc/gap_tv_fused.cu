@@ -37,16 +37,19 @@ using namespace fusedk;
 namespace {
 
 // replay skimage's stopping rule on the accumulated energies
-__global__ void energy_check_kernel(const double* __restrict__ energy, int nslice, int R, double eps,
+__global__ void energy_check_kernel(double* __restrict__ energy, int nslice, int R, double eps,
                                     int* __restrict__ flag) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nslice) return;
-    const double* e = energy + (size_t)s * R;
+    double* e = energy + (size_t)s * R;
     double e_init = e[0], e_prev = e[0];
+    bool fired = false;
     for (int i = 1; i < R; ++i) {             // a stop at i = R (the last iteration) changes nothing
-        if (fabs(e_prev - e[i]) < eps * e_init) { atomicOr(flag, 1); return; }
+        if (fabs(e_prev - e[i]) < eps * e_init) fired = true;
         e_prev = e[i];
     }
+    for (int i = 0; i < R; ++i) e[i] = 0.0;   // leave the accumulators clean for the next launch
+    if (fired) atomicOr(flag, 1);
 }
 
 // ---- TMA descriptors -------------------------------------------------------------------------
@@ -170,7 +173,10 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
         maps.y = maps.x; maps.ps = maps.x; maps.y1 = maps.x;    // unused
     }
 
-    SCIPNP_CUDA(cudaMemsetAsync(fp.energy, 0, (size_t)a.B * a.C * R * sizeof(double), st));
+    // the check kernel leaves the accumulators zeroed; a caller that owns the workspace and always
+    // passes a flag (the solver) therefore clears it once, everybody else per launch
+    if (!(a.workspace_clean && a.flag && R > 1))
+        SCIPNP_CUDA(cudaMemsetAsync(fp.energy, 0, (size_t)a.B * a.C * R * sizeof(double), st));
     int rc = SCIPNP_OK;
     switch (R) {
         case 2: rc = launch_stream_r<2>(a.mode, fp.K, fp, maps, grid, st); break;

@@ -35,6 +35,7 @@ struct FusedArgs {
     int B, H, W, C, phi_batched;
     void* workspace; size_t workspace_bytes;
     int* flag;                // set nonzero if the energy criterion would have fired
+    bool workspace_clean;     // the energy accumulators are known to be zero (see launch_fused)
 };
 bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
 size_t fused_workspace_bytes(int B, int H, int W, int C, int tv_iter_max);

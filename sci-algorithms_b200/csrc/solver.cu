@@ -35,7 +35,7 @@ struct scipnp_solver {
     float *y = nullptr, *Phi = nullptr, *PhiSum = nullptr, *Xorig = nullptr;
     float *xsnap = nullptr, *y1snap = nullptr, *bsnap = nullptr;   // rollback copies (fused)
     void* tvws = nullptr; size_t tvws_bytes = 0;
-    void* fws = nullptr; size_t fws_bytes = 0;
+    void* fws = nullptr; size_t fws_bytes = 0; bool fws_clean = false;
     double* sqerr = nullptr;   // [kPsnrCap]
     int* flags = nullptr;      // [1]
     // host state
@@ -228,6 +228,7 @@ static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
     a.B = p.B; a.H = p.H; a.W = p.W; a.C = p.C; a.phi_batched = p.phi_batched;
     a.workspace = s->fws; a.workspace_bytes = s->fws_bytes;
     a.flag = s->flags;
+    a.workspace_clean = s->fws_clean;
     if (p.method == 0) {
         a.mode = p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN;
         a.y1_in = s->y1a; a.y1_out = s->y1b;
@@ -236,6 +237,7 @@ static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
         a.b_in = s->ba; a.b_out = s->bb; a.xproj_out = s->xproj;
     }
     if (int e = launch_fused(a, st)) return e;
+    s->fws_clean = true;            // the check kernel re-zeroes the accumulators
     std::swap(s->xa, s->xb);
     if (p.method == 0) { if (p.accelerate) std::swap(s->y1a, s->y1b); }
     else std::swap(s->ba, s->bb);
@@ -412,6 +414,54 @@ __global__ void tile_wait_kernel(volatile int* f0, volatile int* f1, int need, i
     __threadfence_system();
 }
 
+// One launch per halo refresh: announce my rows, wait for the neighbours', pull their rows over
+// NVLink (128-bit peer loads), acknowledge.  Regions: up to four (x and y1 from above and below).
+struct PullJob {
+    const float4* src[4];
+    float4* dst[4];
+    long long n4[4];              // float4 count (regions are multiples of 4 floats)
+    int* ready_up; int* ready_dn;     // neighbours' flags I write
+    int* ack_up; int* ack_dn;
+    volatile int* my_ready0; volatile int* my_ready1;   // my flags the neighbours write
+    int* counter;                 // last-CTA detection
+    int* timeout_flag;
+    int epoch;
+};
+
+__global__ void __launch_bounds__(256) tile_exchange_kernel(const PullJob j) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            if (j.ready_up) *reinterpret_cast<volatile int*>(j.ready_up) = j.epoch;
+            if (j.ready_dn) *reinterpret_cast<volatile int*>(j.ready_dn) = j.epoch;
+        }
+        const long long t0 = clock64();
+        while ((j.my_ready0 && *j.my_ready0 < j.epoch) || (j.my_ready1 && *j.my_ready1 < j.epoch)) {
+            __nanosleep(100);
+            if (clock64() - t0 > 16000000000LL) { atomicExch(j.timeout_flag, 1); break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float4* __restrict__ s = j.src[r];
+        float4* __restrict__ d = j.dst[r];
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < j.n4[r]; i += stride) d[i] = s[i];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(j.counter, 1) == (int)gridDim.x - 1) {      // last CTA: everything is pulled
+            *j.counter = 0;
+            __threadfence_system();
+            if (j.ack_up) *reinterpret_cast<volatile int*>(j.ack_up) = j.epoch;
+            if (j.ack_dn) *reinterpret_cast<volatile int*>(j.ack_dn) = j.epoch;
+        }
+    }
+}
+
 constexpr int kIpcBlob = 5 * 64;
 
 }  // namespace
@@ -489,34 +539,47 @@ int scipnp_solver_exchange(scipnp_solver* s, void* stream) {
     const int W = s->p.W, C = s->p.C;
     const int xi = s->xa == s->xbuf[0] ? 0 : 1;
     const int yi = s->y1a == s->y1buf[0] ? 0 : 1;
-    // 1. my rows of this epoch are final: tell the neighbours (I am the upper one's "down" side)
-    tile_signal_kernel<<<1, 1, 0, st>>>(s->up.present ? s->up.sync + 1 : nullptr,
-                                       s->dn.present ? s->dn.sync + 0 : nullptr, e);
-    // 2. wait for theirs
-    tile_wait_kernel<<<1, 1, 0, st>>>(s->up.present ? s->sync + 0 : nullptr, s->dn.present ? s->sync + 1 : nullptr,
-                                     e, s->sync + 4);
-    count_launch(2);
-    // 3. pull my halo rows out of the neighbours' owned rows
+    // one launch: announce my rows (I am the upper neighbour's "down" side), wait for theirs,
+    // pull my halo rows out of their owned rows, acknowledge
     const size_t rowx = (size_t)W * C, rowy = (size_t)W;
+    PullJob j{};
+    int nr = 0;
+    long long total4 = 0;
+    auto add = [&](const float* src, float* dst, size_t nfloat) {
+        j.src[nr] = reinterpret_cast<const float4*>(src);
+        j.dst[nr] = reinterpret_cast<float4*>(dst);
+        j.n4[nr] = (long long)(nfloat / 4);
+        total4 += j.n4[nr];
+        ++nr;
+    };
+    if ((rowy % 4) != 0 || (rowx % 4) != 0) { set_error("tiled exchange needs W %% 4 == 0"); return SCIPNP_EINVAL; }
     if (s->up.present) {
         const int n = s->t_lo - s->t_row_lo, src = s->t_row_lo - s->up.row_lo;
         if (n > 0) {
-            SCIPNP_CUDA(cudaMemcpyAsync(s->xa, s->up.x[xi] + src * rowx, n * rowx * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            if (s->p.accelerate && s->up.y1[yi])
-                SCIPNP_CUDA(cudaMemcpyAsync(s->y1a, s->up.y1[yi] + src * rowy, n * rowy * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            add(s->up.x[xi] + src * rowx, s->xa, n * rowx);
+            if (s->p.accelerate && s->up.y1[yi]) add(s->up.y1[yi] + src * rowy, s->y1a, n * rowy);
         }
     }
     if (s->dn.present) {
         const int n = s->t_row_hi - s->t_hi, dst = s->t_hi - s->t_row_lo, src = s->t_hi - s->dn.row_lo;
         if (n > 0) {
-            SCIPNP_CUDA(cudaMemcpyAsync(s->xa + dst * rowx, s->dn.x[xi] + src * rowx, n * rowx * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            if (s->p.accelerate && s->dn.y1[yi])
-                SCIPNP_CUDA(cudaMemcpyAsync(s->y1a + dst * rowy, s->dn.y1[yi] + src * rowy, n * rowy * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            add(s->dn.x[xi] + src * rowx, s->xa + dst * rowx, n * rowx);
+            if (s->p.accelerate && s->dn.y1[yi]) add(s->dn.y1[yi] + src * rowy, s->y1a + dst * rowy, n * rowy);
         }
     }
-    // 4. acknowledge: the neighbours may overwrite those buffers once they have seen this
-    tile_signal_kernel<<<1, 1, 0, st>>>(s->up.present ? s->up.sync + 3 : nullptr,
-                                       s->dn.present ? s->dn.sync + 2 : nullptr, e);
+    j.ready_up = s->up.present ? s->up.sync + 1 : nullptr;
+    j.ready_dn = s->dn.present ? s->dn.sync + 0 : nullptr;
+    j.ack_up = s->up.present ? s->up.sync + 3 : nullptr;
+    j.ack_dn = s->dn.present ? s->dn.sync + 2 : nullptr;
+    j.my_ready0 = s->up.present ? s->sync + 0 : nullptr;
+    j.my_ready1 = s->dn.present ? s->sync + 1 : nullptr;
+    j.counter = s->sync + 5;
+    j.timeout_flag = s->sync + 4;
+    j.epoch = e;
+    long long ctas = (total4 + 256 * 8 - 1) / (256 * 8);
+    if (ctas < 1) ctas = 1;
+    if (ctas > num_sms()) ctas = num_sms();
+    tile_exchange_kernel<<<(unsigned)ctas, 256, 0, st>>>(j);
     count_launch();
     s->ack_pending = true;
     return check_launch("tile exchange");
