@@ -116,27 +116,35 @@ def device_scene(torch, h, w, c, row0=0, seed=1005):
 
 # -- CPU baseline (oracle port of the reference's NumPy algorithm) ---------------------------
 
-def _cpu_band(args):
+def _band_inputs(rows, seed):
+    """A `rows`-row, full-width band of a config-5-like scene (smooth moving scene, Bernoulli mask)."""
+    from scipnp import synth
+    meas, mask, orig = synth.make_cacti(rows, W, CR, 1, cfg=100 + seed)
+    return meas[:, :, 0] / np.float32(255.), mask, orig / np.float32(255.)
+
+
+def _cpu_band(args, keep=False):
     rows, iters, seed = args
     from oracle import pnp_sci as O
-    rng = np.random.default_rng(seed)
-    mask = (rng.random((rows, W, CR), dtype=np.float32) <= 0.5).astype(np.float32)
-    orig = rng.random((rows, W, CR), dtype=np.float32)
-    y = np.sum(mask * orig, axis=2)
+    y, mask, orig = _band_inputs(rows, seed)
     A = lambda x: O.A_(x, mask)
     At = lambda v: O.At_(v, mask)
     ms = O.phi_sum(mask)
     t0 = time.perf_counter()
-    O.gap_denoise(y, ms, A, At, _lambda=1, accelerate=True, denoiser='tv', iter_max=iters,
-                  tv_weight=TV_WEIGHT, tv_iter_max=TV_ITER, show_iqa=False)
-    return time.perf_counter() - t0
+    x = O.gap_denoise(y, ms, A, At, _lambda=1, accelerate=True, denoiser='tv', iter_max=iters,
+                      tv_weight=TV_WEIGHT, tv_iter_max=TV_ITER, show_iqa=False)[0]
+    dt = time.perf_counter() - t0
+    if keep:
+        return dt, (y, mask, orig, x)
+    return dt
 
 
 def cpu_baseline(rows=96, iters=2, procs=1):
     """Full-scene-equivalent outer it/s of the NumPy reference algorithm on `procs`
     host processes, each reconstructing its own `rows`-row full-width band."""
+    kept = None
     if procs <= 1:
-        dt = _cpu_band((rows, iters, 1))
+        dt, kept = _cpu_band((rows, iters, 1), keep=True)
         wall = dt
     else:
         import multiprocessing as mp
@@ -146,7 +154,26 @@ def cpu_baseline(rows=96, iters=2, procs=1):
             wall = time.perf_counter() - t0
     rows_total = rows * max(1, procs)
     its = iters * (rows_total / float(H)) / wall
+    cpu_baseline.last_band = kept
     return its, wall
+
+
+def parity_on_band(iters):
+    """max |x_gpu - x_cpu| and PSNR delta on the band the cpu_baseline leg just reconstructed
+    (same inputs, same iteration count); the oracle is the checker here, not the thing measured."""
+    from oracle import pnp_sci as O
+    from scipnp.engine import Solver
+    y, mask, orig, x_cpu = cpu_baseline.last_band
+    with Solver(1, y.shape[0], W, CR, method="gap", accelerate=True, _lambda=1.0, tv_weight=TV_WEIGHT,
+                tv_iter_max=TV_ITER) as s:
+        s.load(y[None], mask)
+        s.run(iters)
+        x_gpu = s.get_x()[0]
+        path = "fused" if s.uses_fused else "exact"
+    p_cpu, p_gpu = O.psnr(orig, x_cpu), O.psnr(orig, x_gpu)
+    return {"max_abs_err": float(np.abs(x_gpu - x_cpu).max()), "psnr_cpu_db": float(p_cpu),
+            "psnr_gpu_db": float(p_gpu), "psnr_delta_db": float(abs(p_gpu - p_cpu)), "iterations": iters,
+            "rows": int(y.shape[0]), "path": path, "tolerance": "max abs <= 1e-4, |dPSNR| <= 0.01 dB"}
 
 
 def run_reference(args):
@@ -299,6 +326,7 @@ def run_ours(args):
     achieved = bytes_it / (iter_ms * 1e-3) / 1e9 / world     # per GPU
     cpu_val, cpu_wall = (None, None)
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu:
         rows, cit = 192, 12
         cpu_val, cpu_wall = cpu_baseline(rows, cit, 1)
@@ -306,6 +334,7 @@ def run_ours(args):
                "sample": "%d-row x %d x %d band of the scene, %d outer iterations, %.1f s of NumPy "
                          "(reference algorithm, oracle port; NumPy elementwise is single-threaded); "
                          "value scaled to the full scene by rows" % (rows, W, CR, cit, cpu_wall)}
+        parity = parity_on_band(cit)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -324,6 +353,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_iteration": bytes_it,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu,
+        "parity": parity,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": sampler.summary() if sampler else None,

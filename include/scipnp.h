@@ -159,6 +159,13 @@ int scipnp_solver_load(scipnp_solver *s, const float *y, const float *Phi,
                        const float *Phi_sum, const float *x0, const float *X_orig,
                        void *stream);
 
+/* R9  CASSI (DeSCI/test_desci_cassi.m:53-75): load a single-disperser measurement.  The handle's W
+ * is the sheared canvas width; `mask2d` is the coded aperture [H][W-(C-1)*step] (host or device).
+ * The fused iterations read the aperture at per-band index offsets, Phi[h,w,c] = M[h, w-step*c],
+ * instead of streaming a shifted mask stack from HBM.                                       */
+int scipnp_solver_load_cassi(scipnp_solver *s, const float *y, const float *mask2d, int step,
+                             const float *x0, const float *X_orig, void *stream);
+
 /* Run `iters` outer iterations on `stream`.  On the fused path the call returns
  * after the stream has drained (it has to look at the early-stop flag and, if it
  * is raised, redoes the run on the exact path); on the exact path it is

@@ -112,6 +112,10 @@ bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max) {
     return true;
 }
 
+bool fused_cassi_supported(int mode, int B, int H, int W, int C, int tv_iter_max) {
+    return fused_supported(mode, B, H, W, C, tv_iter_max) && tv_iter_max == 5;   // built for R = 4
+}
+
 size_t fused_workspace_bytes(int B, int H, int W, int C, int tv_iter_max) {
     (void)H; (void)W;
     int R = tv_iter_max > 1 ? tv_iter_max - 1 : 1;
@@ -124,7 +128,12 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
                   a.mode, a.C, a.tv_iter_max);
         return SCIPNP_EINVAL;
     }
-    if (!aligned16(a.x_in) || !aligned16(a.x_out) || !aligned16(a.Phi)) {
+    const bool cassi = a.mask2d != nullptr;
+    if (cassi && !fused_cassi_supported(a.mode, a.B, a.H, a.W, a.C, a.tv_iter_max)) {
+        set_error("fused CASSI kernel is built for tv_iter_max = 5 only");
+        return SCIPNP_EINVAL;
+    }
+    if (!aligned16(a.x_in) || !aligned16(a.x_out) || (!cassi && !aligned16(a.Phi))) {
         set_error("fused GAP-TV kernel needs 16-byte aligned frame pointers");
         return SCIPNP_EINVAL;
     }
@@ -160,7 +169,9 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     alignas(64) FusedMaps maps;
     const long long rows = (long long)a.B * a.H, phi_rows = a.phi_batched ? rows : a.H;
     if (int e = make_frame_map(&maps.x, a.x_in, rows, a.W, a.C)) return e;
-    if (int e = make_frame_map(&maps.phi, a.Phi, phi_rows, a.W, a.C)) return e;
+    if (cassi) maps.phi = maps.x;          // unused
+    else if (int e = make_frame_map(&maps.phi, a.Phi, phi_rows, a.W, a.C)) return e;
+    const CassiParams cp{a.mask2d, a.cassi_step, a.mask_w};
     // plane boxes start at pixel grp*(32-2R) - R: the TMA unit needs that start 16-byte aligned,
     // which holds for R = 4 (tv_iter_max = 5, the reference's setting); otherwise cp.async
     fp.small_tma = (a.W % 4 == 0) && (R % 4 == 0) && aligned16(a.y) && aligned16(a.Phi_sum) &&
@@ -178,7 +189,8 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     if (!(a.workspace_clean && a.flag && R > 1))
         SCIPNP_CUDA(cudaMemsetAsync(fp.energy, 0, (size_t)a.B * a.C * R * sizeof(double), st));
     int rc = SCIPNP_OK;
-    switch (R) {
+    if (cassi) rc = launch_stream_cassi_r4(a.mode, fp.K, fp, maps, cp, grid, st);
+    else switch (R) {
         case 2: rc = launch_stream_r<2>(a.mode, fp.K, fp, maps, grid, st); break;
         case 3: rc = launch_stream_r<3>(a.mode, fp.K, fp, maps, grid, st); break;
         case 4: rc = launch_stream_r<4>(a.mode, fp.K, fp, maps, grid, st); break;

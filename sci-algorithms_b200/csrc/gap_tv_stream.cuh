@@ -25,6 +25,10 @@ struct FusedParams {
     long long phi_bstride, ps_bstride;   // batch strides (0 when shared)
 };
 
+// CASSI (template flag): Phi[h, w, c] = mask2d[h, w - step*c] on a canvas of W columns.  Kept out of
+// FusedParams on purpose: ptxas' register allocation of the main kernel is sensitive to that layout.
+struct CassiParams { const float* mask2d; int step, mask_w; };
+
 // tensor maps of one launch: x_in and Phi as [rows][W][K][4 floats] (box RB x 32 x 1 x 4, i.e. the
 // transposition to chunk-major tiles is done by the TMA unit), y / y1_in / Phi_sum as [rows][W]
 struct FusedMaps { CUtensorMap x, phi, y, y1, ps; };
@@ -202,9 +206,9 @@ __device__ __forceinline__ void pipe_step(Pipe<R>& S, const StepConst& c, int rh
     S.fd[0][1] = f_new[1];
 }
 
-template <int R, int MODE, bool CHECK, int K>
+template <int R, int MODE, bool CHECK, int K, bool CASSI>
 __global__ void __launch_bounds__(fused_threads(K), 2)
-gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps) {
+gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps, const CassiParams cp) {
     constexpr int NG = fused_groups(K);
     constexpr int NT = fused_threads(K);
     constexpr Smem L = smem_layout(K, NG);
@@ -261,7 +265,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     //      2*NG*K boxes of x / Phi (+ 3*NG rows of y, y1, Phi_sum) land in slot blk % 3 and
     //      complete on that slot's mbarrier.  Pixels left/right of the image are zero-filled by
     //      the TMA unit; rows past the segment are loaded but never used.
-    constexpr uint32_t kTileTx = 2u * NG * K * BOX_BYTES;
+    constexpr uint32_t kTileTx = (CASSI ? 1u : 2u) * NG * K * BOX_BYTES;   // CASSI: no Phi stack to load
     constexpr uint32_t kSmallTx = (MODE == MODE_GAP_ACC ? 3u : 2u) * NG * RB * 32 * 4;
     const int rowc0 = b * H;                              // row coordinate of the batch element
     const int phirow0 = p.phi_batched ? b * H : 0;
@@ -282,7 +286,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
                     for (int kk = 0; kk < K; ++kk) {
                         const uint32_t d = dst + (g2 * K + kk) * BOX_BYTES;
                         tma_load_4d(d, &maps.x, 0, kk, px0, rowc0 + row0, bar);
-                        tma_load_4d(d + L.tile_bytes, &maps.phi, 0, kk, px0, phirow0 + row0, bar);
+                        if constexpr (!CASSI) tma_load_4d(d + L.tile_bytes, &maps.phi, 0, kk, px0, phirow0 + row0, bar);
                     }
                     if (p.small_tma) {
                         const uint32_t ds = dst + L.small_off + g2 * RB * 128;
@@ -317,6 +321,22 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     auto wait_block = [&](int blk) {       // tiles (and TMA-staged rows) of block blk have landed
         if (blk < nblk) mbar_wait(bar_base + ((gb + blk) % NSLOT) * 8, ((gb + blk) / NSLOT) & 1);
     };
+    // Phi of this thread's 4 channels at (row, px): from the staged tile, or -- CASSI -- the 2-D coded
+    // aperture read at the per-band offset (the dispersion shift is an index offset, no stack in HBM)
+    auto load_phi = [&](const float4* tx, int row) -> float4 {
+        if constexpr (!CASSI) {
+            return tx[L.tile_bytes / 16];          // same slot layout as x, one tile further
+        } else {
+            float v[4];
+            const float* mrow = cp.mask2d + ((size_t)(p.phi_batched ? b : 0) * H + min(row, H - 1)) * cp.mask_w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int wm = px - cp.step * (4 * k + i);
+                v[i] = (px_in && row < H && wm >= 0 && wm < cp.mask_w) ? __ldg(mrow + wm) : 0.f;
+            }
+            return make_float4(v[0], v[1], v[2], v[3]);
+        }
+    };
     // partial dot products of this warp's chunk for the rows of block `blk`
     auto phase_a = [&](int blk) {
         if (blk >= nblk) return;
@@ -327,7 +347,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         for (int j = 0; j < RB; ++j) {           // all loads first: one shared-memory round trip
             const float4* tx = reinterpret_cast<const float4*>(buf + (gi * K + k) * BOX_BYTES) + j * 32 + lane;
             xv[j] = tx[0];
-            pv[j] = tx[L.tile_bytes / 16];
+            pv[j] = load_phi(tx, rs + blk * RB + j);
         }
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
@@ -369,7 +389,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     // stage 0 of step rho (row j of the block in `buf`): Euclidean projection -> f(rho)
     auto project_row = [&](const unsigned char* buf, const float* part, int j, int rho, P2 (&f_new)[2]) {
         const float4* tx = reinterpret_cast<const float4*>(buf + (gi * K + k) * BOX_BYTES) + j * 32 + lane;
-        const float4 xv = tx[0], pv = tx[L.tile_bytes / 16];
+        const float4 xv = tx[0], pv = load_phi(tx, rho);
         const float4* pp = reinterpret_cast<const float4*>(part + ((j * NG + gi) * 32 + lane) * L.KP);
         float yb = 0.f;
 #pragma unroll
@@ -454,10 +474,13 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
 
 // one launcher per R, defined in fused_inst_r{2,3,4}.cu
 template <int R> int launch_stream_r(int mode, int K, const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st);
+// CASSI variants (index-offset mask), built for R = 4 only: fused_inst_r4c.cu
+int launch_stream_cassi_r4(int mode, int K, const FusedParams& fp, const FusedMaps& maps, const CassiParams& cp,
+                           dim3 grid, cudaStream_t st);
 
-template <int R, int MODE, int K>
-int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream_t st) {
-    auto kfn = gap_tv_stream_kernel<R, MODE, true, K>;
+template <int R, int MODE, int K, bool CASSI = false>
+int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream_t st, CassiParams cp = CassiParams{nullptr, 0, 0}) {
+    auto kfn = gap_tv_stream_kernel<R, MODE, true, K, CASSI>;
     constexpr Smem L = smem_layout(K, fused_groups(K));
     static int ctas_per_sm = 0;            // resident CTAs of this instance, queried once
     if (!ctas_per_sm) {
@@ -475,23 +498,24 @@ int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream
     if (n > slots) n = slots;
     if (n < 1) n = 1;
     grid = dim3((unsigned)n, 1, 1);
-    kfn<<<grid, fused_threads(K), L.total, st>>>(fp, maps);
+    kfn<<<grid, fused_threads(K), L.total, st>>>(fp, maps, cp);
     return SCIPNP_OK;
 }
 
-template <int R, int MODE>
-int launch_stream_mode(int K, const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st) {
+template <int R, int MODE, bool CASSI = false>
+int launch_stream_mode(int K, const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st,
+                       CassiParams cp = CassiParams{nullptr, 0, 0}) {
     switch (K) {
 #ifndef SCIPNP_FUSED_FAST_BUILD
-        case 1: return launch_stream_k<R, MODE, 1>(fp, maps, grid, st);
-        case 3: return launch_stream_k<R, MODE, 3>(fp, maps, grid, st);
-        case 4: return launch_stream_k<R, MODE, 4>(fp, maps, grid, st);
-        case 5: return launch_stream_k<R, MODE, 5>(fp, maps, grid, st);
-        case 7: return launch_stream_k<R, MODE, 7>(fp, maps, grid, st);
-        case 8: return launch_stream_k<R, MODE, 8>(fp, maps, grid, st);
+        case 1: return launch_stream_k<R, MODE, 1, CASSI>(fp, maps, grid, st, cp);
+        case 3: return launch_stream_k<R, MODE, 3, CASSI>(fp, maps, grid, st, cp);
+        case 4: return launch_stream_k<R, MODE, 4, CASSI>(fp, maps, grid, st, cp);
+        case 5: return launch_stream_k<R, MODE, 5, CASSI>(fp, maps, grid, st, cp);
+        case 7: return launch_stream_k<R, MODE, 7, CASSI>(fp, maps, grid, st, cp);
+        case 8: return launch_stream_k<R, MODE, 8, CASSI>(fp, maps, grid, st, cp);
 #endif
-        case 2: return launch_stream_k<R, MODE, 2>(fp, maps, grid, st);
-        case 6: return launch_stream_k<R, MODE, 6>(fp, maps, grid, st);
+        case 2: return launch_stream_k<R, MODE, 2, CASSI>(fp, maps, grid, st, cp);
+        case 6: return launch_stream_k<R, MODE, 6, CASSI>(fp, maps, grid, st, cp);
     }
     set_error("fused kernel not built for C = %d", 4 * K);
     return SCIPNP_EINVAL;

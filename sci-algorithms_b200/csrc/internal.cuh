@@ -36,8 +36,11 @@ struct FusedArgs {
     void* workspace; size_t workspace_bytes;
     int* flag;                // set nonzero if the energy criterion would have fired
     bool workspace_clean;     // the energy accumulators are known to be zero (see launch_fused)
+    // CASSI: Phi == nullptr and the coded aperture mask2d [H][mask_w] is read at offset step*c
+    const float* mask2d; int cassi_step; int mask_w;
 };
 bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
+bool fused_cassi_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
 size_t fused_workspace_bytes(int B, int H, int W, int C, int tv_iter_max);
 int launch_fused(const FusedArgs& a, cudaStream_t st);
 

@@ -42,6 +42,8 @@ struct scipnp_solver {
     bool loaded = false, has_orig = false, use_fused = false;
     int iters_done = 0, psnr_count = 0, refined = 0, begin_iter = 0;
     bool fused_possible = false;
+    // CASSI: coded aperture [H][mask_w]; the fused kernel reads it at per-band offsets
+    bool cassi = false; float* mask2d = nullptr; int cassi_step = 0, mask_w = 0;
     long long launches0 = 0;
     std::vector<void*> owned;
     // ---- row-tiled multi-GPU mode: direct peer access to the neighbours' buffers ----
@@ -160,8 +162,9 @@ int scipnp_solver_load(scipnp_solver* s, const float* y, const float* Phi, const
     SCIPNP_REQUIRE(s && y && Phi, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const scipnp_params& p = s->p;
+    s->cassi = false;
     SCIPNP_CUDA(cudaMemcpyAsync(s->y, y, s->n_meas * sizeof(float), cudaMemcpyDefault, st));
-    SCIPNP_CUDA(cudaMemcpyAsync(s->Phi, Phi, s->n_phi * sizeof(float), cudaMemcpyDefault, st));
+    if (Phi != s->Phi) SCIPNP_CUDA(cudaMemcpyAsync(s->Phi, Phi, s->n_phi * sizeof(float), cudaMemcpyDefault, st));
     if (Phi_sum) {
         SCIPNP_CUDA(cudaMemcpyAsync(s->PhiSum, Phi_sum, s->n_phisum * sizeof(float), cudaMemcpyDefault, st));
     } else {
@@ -186,6 +189,30 @@ int scipnp_solver_load(scipnp_solver* s, const float* y, const float* Phi, const
     s->iters_done = 0;
     s->psnr_count = 0;
     s->refined = 0;
+    return SCIPNP_OK;
+}
+
+// R9: CASSI.  `mask2d` is the coded aperture [H][W-(C-1)*step]; the solver's W is the sheared canvas.
+int scipnp_solver_load_cassi(scipnp_solver* s, const float* y, const float* mask2d, int step,
+                             const float* x0, const float* X_orig, void* stream) {
+    SCIPNP_REQUIRE(s && y && mask2d, "null pointer");
+    const scipnp_params& p = s->p;
+    SCIPNP_REQUIRE(p.B == 1 && !p.phi_batched, "CASSI mode takes one measurement (B = 1)");
+    SCIPNP_REQUIRE(step >= 0 && p.W - (p.C - 1) * step >= 1, "canvas narrower than the dispersion");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mw = p.W - (p.C - 1) * step;
+    if (!s->mask2d || s->mask_w != mw) {
+        if (int e = dmalloc(s, (void**)&s->mask2d, (size_t)p.H * mw * sizeof(float))) return e;
+    }
+    s->mask_w = mw;
+    s->cassi_step = step;
+    SCIPNP_CUDA(cudaMemcpyAsync(s->mask2d, mask2d, (size_t)p.H * mw * sizeof(float), cudaMemcpyDefault, st));
+    // the explicit stack is built once (initial guess, Phi_sum, exact-path fallback); the fused
+    // iterations never read it
+    if (int e = scipnp_cassi_shift_mask(s->mask2d, s->Phi, p.H, mw, p.C, step, stream)) return e;
+    if (int e = scipnp_solver_load(s, y, s->Phi, nullptr, x0, X_orig, stream)) return e;
+    const int mode = p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN;
+    s->cassi = p.method == 0 && fused_cassi_supported(mode, p.B, p.H, p.W, p.C, p.tv_iter_max);
     return SCIPNP_OK;
 }
 
@@ -223,6 +250,7 @@ static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
     FusedArgs a{};
     a.x_in = s->xa; a.x_out = s->xb;
     a.y = s->y; a.Phi = s->Phi; a.Phi_sum = s->PhiSum;
+    if (s->cassi) { a.Phi = nullptr; a.mask2d = s->mask2d; a.cassi_step = s->cassi_step; a.mask_w = s->mask_w; }
     a.lambda = p.lambda; a.gamma = p.gamma;
     a.tv_weight = p.tv_weight; a.tv_eps = p.tv_eps; a.tv_iter_max = p.tv_iter_max;
     a.B = p.B; a.H = p.H; a.W = p.W; a.C = p.C; a.phi_batched = p.phi_batched;

@@ -127,6 +127,21 @@ class Solver:
             torch.cuda.current_stream().synchronize()   # pageable host sources
         self._keep = []
 
+    def load_cassi(self, y, mask2d, step, x0=None, X_orig=None):
+        """Single-disperser CASSI (B = 1): ``mask2d`` [H, W-(C-1)*step] is the coded aperture, the
+        solver's W the sheared canvas; the fused iterations read the aperture at per-band offsets."""
+        B, H, W, Cc = self.shape
+        self._keep = []
+        y = self._chk(y, (B, H, W), "y")
+        mask2d = self._chk(mask2d, (H, W - (Cc - 1) * int(step)), "mask2d")
+        x0 = self._chk(x0, (B, H, W, Cc), "x0")
+        X_orig = self._chk(X_orig, (B, H, W, Cc), "X_orig")
+        check(lib.scipnp_solver_load_cassi(self._h, dptr(y), dptr(mask2d), int(step), dptr(x0),
+                                           dptr(X_orig), stream_ptr()))
+        if any(not is_torch(a) for a in self._keep):
+            torch.cuda.current_stream().synchronize()
+        self._keep = []
+
     def run(self, iters):
         check(lib.scipnp_solver_run(self._h, int(iters), stream_ptr()))
 

@@ -256,20 +256,34 @@ def gap_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, accelerate=True, denoiser='
 
 # -- R9 ------------------------------------------------------------------------
 
-def gap_denoise_cassi(y, mask2d, nband, step, **kw):
-    """GAP-TV for single-disperser CASSI (DeSCI/test_desci_cassi.m:53-75): the
-    coded aperture ``mask2d`` [H, W] is sheared by ``step`` pixels per band on the
-    device (``Phi[h, w+step*k, k] = M[h, w]``) and the reconstruction runs on the
-    sheared canvas [H, W+(nband-1)*step, nband], as the reference's data are."""
-    m = to_device(f32c(_host(mask2d)))
+def gap_denoise_cassi(y, mask2d, nband, step, _lambda=1, accelerate=True, denoiser='tv',
+                      iter_max=50, noise_estimate=False, sigma=None, tv_weight=0.1, tv_iter_max=5,
+                      multichannel=True, x0=None, X_orig=None, model=None, show_iqa=True,
+                      tvm='tv_chambolle'):
+    """GAP-TV for single-disperser CASSI (DeSCI/test_desci_cassi.m:53-75).  The coded aperture
+    ``mask2d`` [H, W] is dispersed by ``step`` pixels per band (``Phi[h, w+step*k, k] = M[h, w]``)
+    and the reconstruction runs on the sheared canvas [H, W+(nband-1)*step, nband], as the
+    reference's data are.  The iterations read the aperture at per-band index offsets; the shifted
+    mask stack is only built once on the device for the initial guess and ``Phi_sum``.
+    Returns ``(x, psnr_, ssim_, psnr_all)`` like ``gap_denoise``."""
+    _check_tv(denoiser, tvm, multichannel)
+    m = f32c(_host(mask2d))
     H, W = m.shape
     Wc = W + (nband - 1) * step
-    Phi = torch.empty((H, Wc, nband), dtype=torch.float32, device=m.device)
-    check(lib.scipnp_cassi_shift_mask(dptr(m), dptr(Phi), H, W, nband, step, stream_ptr()))
-    Phi_h = Phi.cpu().numpy()
-    ms = np.sum(Phi_h, axis=2)
-    ms[ms == 0] = 1
-    return gap_denoise(y, ms, Phi=Phi_h, **kw)
+    yh = f32c(_host(y))
+    if yh.shape != (H, Wc):
+        raise ValueError("y has shape %s, expected the sheared canvas %s" % (yh.shape, (H, Wc)))
+    Xo = None if X_orig is None else f32c(_host(X_orig))
+    with Solver(1, H, Wc, nband, method="gap", accelerate=accelerate, _lambda=_lambda,
+                tv_weight=tv_weight, tv_iter_max=tv_iter_max, fused=USE_FUSED) as s:
+        s.load_cassi(yh[None], m, step, x0=None if x0 is None else f32c(_host(x0))[None],
+                     X_orig=None if (Xo is None or not show_iqa) else Xo[None])
+        s.run(_total_iters(sigma, iter_max))
+        x = s.get_x()[0]
+        pa = [float(v) for v in s.psnr_all()[:, 0]]
+    _progress('GAP', pa)
+    ps, ss = frames_iqa(Xo, x)
+    return x, ps, ss, pa
 
 
 # -- R6 ------------------------------------------------------------------------
