@@ -91,3 +91,47 @@ def test_single_rank_exchange_is_a_no_op():
     f = torch.arange(12.).reshape(4, 3)
     exchange_halos([f], 4, 2, 0, 1)
     assert torch.equal(f, torch.arange(12.).reshape(4, 3))
+
+
+# -- independent measurements sharded over ranks (gloo) ------------------------------------------------
+
+def _shard_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pnp_sci as O
+        from scipnp import synth
+        from scipnp.sharded import admmdenoise_cacti_sharded
+        meas, mask, orig = synth.make_cacti(24, 20, 4, 5, cfg=41)
+        A = lambda x: O.A_(x, mask)
+        At = lambda v: O.At_(v, mask)
+        res = admmdenoise_cacti_sharded(meas, mask, A, At, projmeth='gap', orig=orig, nframe=5, MAXB=255.,
+                                        maskdirection='updown', solve=O.admmdenoise_cacti, _lambda=1,
+                                        accelerate=True, denoiser='tv', iter_max=4, tv_weight=0.3,
+                                        tv_iter_max=5)
+        np.save(os.path.join(out_dir, "x_%d.npy" % rank), res[0])
+        np.save(os.path.join(out_dir, "p_%d.npy" % rank), np.array(res[2]))
+        np.save(os.path.join(out_dir, "pa_%d.npy" % rank), np.array(res[4]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_measurements_equal_single_process(tmp_path):
+    from oracle import pnp_sci as O
+    from scipnp import synth
+    from scipnp.sharded import shard_indices
+    world = 2
+    mp.spawn(_shard_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    meas, mask, orig = synth.make_cacti(24, 20, 4, 5, cfg=41)
+    A = lambda x: O.A_(x, mask)
+    At = lambda v: O.At_(v, mask)
+    ref = O.admmdenoise_cacti(meas, mask, A, At, projmeth='gap', orig=orig, nframe=5, MAXB=255.,
+                              maskdirection='updown', _lambda=1, accelerate=True, denoiser='tv',
+                              iter_max=4, tv_weight=0.3, tv_iter_max=5)
+    for r in range(world):                 # every rank holds the complete, identical result
+        np.testing.assert_array_equal(np.load(tmp_path / ("x_%d.npy" % r)), ref[0])
+        np.testing.assert_array_equal(np.load(tmp_path / ("p_%d.npy" % r)), np.array(ref[2]))
+        np.testing.assert_array_equal(np.load(tmp_path / ("pa_%d.npy" % r)), np.array(ref[4]))
+    assert shard_indices(5, 2, 0) == [0, 2, 4] and shard_indices(5, 2, 1) == [1, 3]
+    assert sorted(shard_indices(28, 8, 3)) == [3, 11, 19, 27]
