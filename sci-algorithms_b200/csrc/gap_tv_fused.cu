@@ -105,7 +105,7 @@ int make_plane_map(CUtensorMap* tm, const float* base, long long rows, int W) {
 }  // namespace
 
 bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max) {
-    if (mode != MODE_GAP_ACC && mode != MODE_GAP_PLAIN) return false;   // ADMM: exact path
+    if (mode != MODE_GAP_ACC && mode != MODE_GAP_PLAIN && mode != MODE_ADMM) return false;
     if (C % 4 != 0 || C / 4 > kMaxWarps) return false;
     if (tv_iter_max < 3 || tv_iter_max > 5) return false;      // R = 2..4 are instantiated
     if (B < 1 || B > 65535 || H < 1 || W < 1) return false;
@@ -113,7 +113,7 @@ bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max) {
 }
 
 bool fused_cassi_supported(int mode, int B, int H, int W, int C, int tv_iter_max) {
-    return fused_supported(mode, B, H, W, C, tv_iter_max) && tv_iter_max == 5;   // built for R = 4
+    return mode != MODE_ADMM && fused_supported(mode, B, H, W, C, tv_iter_max) && tv_iter_max == 5;   // R = 4 only
 }
 
 size_t fused_workspace_bytes(int B, int H, int W, int C, int tv_iter_max) {
@@ -171,7 +171,11 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     if (int e = make_frame_map(&maps.x, a.x_in, rows, a.W, a.C)) return e;
     if (cassi) maps.phi = maps.x;          // unused
     else if (int e = make_frame_map(&maps.phi, a.Phi, phi_rows, a.W, a.C)) return e;
-    const CassiParams cp{a.mask2d, a.cassi_step, a.mask_w};
+    const CassiParams cp{a.mask2d, a.cassi_step, a.mask_w, a.b_in, a.b_out, a.xproj_out, a.gamma};
+    if (a.mode == MODE_ADMM && (!a.b_in || !a.b_out || !a.xproj_out || a.b_in == a.b_out || !aligned16(a.b_in))) {
+        set_error("fused ADMM-TV needs distinct, aligned multiplier buffers and an x output");
+        return SCIPNP_EINVAL;
+    }
     // plane boxes start at pixel grp*(32-2R) - R: the TMA unit needs that start 16-byte aligned,
     // which holds for R = 4 (tv_iter_max = 5, the reference's setting); otherwise cp.async
     fp.small_tma = (a.W % 4 == 0) && (R % 4 == 0) && aligned16(a.y) && aligned16(a.Phi_sum) &&
@@ -191,9 +195,9 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     int rc = SCIPNP_OK;
     if (cassi) rc = launch_stream_cassi_r4(a.mode, fp.K, fp, maps, cp, grid, st);
     else switch (R) {
-        case 2: rc = launch_stream_r<2>(a.mode, fp.K, fp, maps, grid, st); break;
-        case 3: rc = launch_stream_r<3>(a.mode, fp.K, fp, maps, grid, st); break;
-        case 4: rc = launch_stream_r<4>(a.mode, fp.K, fp, maps, grid, st); break;
+        case 2: rc = launch_stream_r<2>(a.mode, fp.K, fp, maps, cp, grid, st); break;
+        case 3: rc = launch_stream_r<3>(a.mode, fp.K, fp, maps, cp, grid, st); break;
+        case 4: rc = launch_stream_r<4>(a.mode, fp.K, fp, maps, cp, grid, st); break;
         default: set_error("unsupported tv_iter_max"); return SCIPNP_EINVAL;
     }
     if (rc) return rc;

@@ -27,7 +27,11 @@ struct FusedParams {
 
 // CASSI (template flag): Phi[h, w, c] = mask2d[h, w - step*c] on a canvas of W columns.  Kept out of
 // FusedParams on purpose: ptxas' register allocation of the main kernel is sensitive to that layout.
-struct CassiParams { const float* mask2d; int step, mask_w; };
+struct CassiParams {
+    const float* mask2d; int step, mask_w;
+    // ADMM (MODE_ADMM): multiplier in/out, projection output x (returned by admm_denoise), gamma
+    const float* b_in; float* b_out; float* xproj; float gamma;
+};
 
 // tensor maps of one launch: x_in and Phi as [rows][W][K][4 floats] (box RB x 32 x 1 x 4, i.e. the
 // transposition to chunk-major tiles is done by the TMA unit), y / y1_in / Phi_sum as [rows][W]
@@ -348,6 +352,13 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
             const float4* tx = reinterpret_cast<const float4*>(buf + (gi * K + k) * BOX_BYTES) + j * 32 + lane;
             xv[j] = tx[0];
             pv[j] = load_phi(tx, rs + blk * RB + j);
+            if constexpr (MODE == MODE_ADMM) {          // the projection acts on u = theta + b
+                const int row = rs + blk * RB + j;
+                if (px_in && row < H) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(cp.b_in + frame_b + ((size_t)row * W + px) * C + 4 * k));
+                    xv[j].x += bv.x; xv[j].y += bv.y; xv[j].z += bv.z; xv[j].w += bv.w;
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
@@ -402,16 +413,33 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
             const float y1n = sm[NG * RB * 32] + (yv - yb);
             if (k == 0 && own_px && rho >= r0 && rho < r1) y1o[(size_t)rho * W + px] = y1n;
             s = __fdividef(y1n - yb, psv);
+        } else if (MODE == MODE_ADMM) {
+            s = __fdividef(yv - yb, psv + cp.gamma);      // pnp_sci_algo.py:809
         } else {
             s = __fdividef(yv - yb, psv);
         }
         const P2 s2 = splat(px_in ? s * lam : 0.f);
         f_new[0] = fma2(s2, make_float2(pv.x, pv.y), make_float2(xv.x, xv.y));
         f_new[1] = fma2(s2, make_float2(pv.z, pv.w), make_float2(xv.z, xv.w));
+        if constexpr (MODE == MODE_ADMM) {
+            // f = x - b = theta + lambda*s*Phi is the TV input; x = f + b is what admm_denoise returns
+            if (own_px && rho >= r0 && rho < r1) {
+                const size_t o = frame_b + ((size_t)rho * W + px) * C + 4 * k;
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(cp.b_in + o));
+                *reinterpret_cast<float4*>(cp.xproj + o) =
+                    make_float4(f_new[0].x + bv.x, f_new[0].y + bv.y, f_new[1].x + bv.z, f_new[1].y + bv.w);
+            }
+        }
     };
-    auto store_row = [&](int orow, const P2 (&o)[2]) {
-        if (own_px && orow >= r0 && orow < r1)
+    // f_out = f(orow), the value that left the f delay line in this step: the ADMM multiplier update
+    // b - (x - theta_new) equals theta_new - f  (pnp_sci_algo.py:836 with x = f + b)
+    auto store_row = [&](int orow, const P2 (&o)[2], const P2 (&f_out)[2]) {
+        if (own_px && orow >= r0 && orow < r1) {
             *reinterpret_cast<float4*>(xo + ((size_t)orow * W + px) * C + 4 * k) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+            if constexpr (MODE == MODE_ADMM)
+                *reinterpret_cast<float4*>(cp.b_out + frame_b + ((size_t)orow * W + px) * C + 4 * k) =
+                    make_float4(o[0].x - f_out[0].x, o[0].y - f_out[0].y, o[1].x - f_out[1].x, o[1].y - f_out[1].y);
+        }
     };
 
     issue(0);
@@ -436,8 +464,9 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
                 const int rho = rho0 + j;
                 P2 f_new[2], o_new[2];
                 project_row(buf, part, j, rho, f_new);
+                const P2 f_out[2] = {S.fd[R - 1][0], S.fd[R - 1][1]};
                 pipe_step<R, CHECK, true>(S, sc, rho, f_new, o_new);
-                store_row(rho - R, o_new);
+                store_row(rho - R, o_new, f_out);
             }
         } else {
 #pragma unroll 1
@@ -446,8 +475,9 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
                 if (rho < rend) {
                     P2 f_new[2] = {zero2, zero2}, o_new[2];
                     if (rho < H) project_row(buf, part, j, rho, f_new);
+                    const P2 f_out[2] = {S.fd[R - 1][0], S.fd[R - 1][1]};
                     pipe_step<R, CHECK, false>(S, sc, rho, f_new, o_new);
-                    store_row(rho - R, o_new);
+                    store_row(rho - R, o_new, f_out);
                 }
             }
         }
@@ -473,7 +503,8 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
 }
 
 // one launcher per R, defined in fused_inst_r{2,3,4}.cu
-template <int R> int launch_stream_r(int mode, int K, const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st);
+template <int R> int launch_stream_r(int mode, int K, const FusedParams& fp, const FusedMaps& maps, const CassiParams& cp,
+                                     dim3 grid, cudaStream_t st);
 // CASSI variants (index-offset mask), built for R = 4 only: fused_inst_r4c.cu
 int launch_stream_cassi_r4(int mode, int K, const FusedParams& fp, const FusedMaps& maps, const CassiParams& cp,
                            dim3 grid, cudaStream_t st);
@@ -523,9 +554,10 @@ int launch_stream_mode(int K, const FusedParams& fp, const FusedMaps& maps, dim3
 
 #define SCIPNP_INSTANTIATE_FUSED_R(RR)                                                                 \
     template <> int launch_stream_r<RR>(int mode, int K, const FusedParams& fp, const FusedMaps& maps, \
-                                        dim3 grid, cudaStream_t st) {                                  \
-        if (mode == MODE_GAP_ACC) return launch_stream_mode<RR, MODE_GAP_ACC>(K, fp, maps, grid, st); \
-        return launch_stream_mode<RR, MODE_GAP_PLAIN>(K, fp, maps, grid, st);                          \
+                                        const CassiParams& cp, dim3 grid, cudaStream_t st) {           \
+        if (mode == MODE_GAP_ACC) return launch_stream_mode<RR, MODE_GAP_ACC>(K, fp, maps, grid, st, cp);   \
+        if (mode == MODE_ADMM) return launch_stream_mode<RR, MODE_ADMM>(K, fp, maps, grid, st, cp);         \
+        return launch_stream_mode<RR, MODE_GAP_PLAIN>(K, fp, maps, grid, st, cp);                          \
     }
 
 }  // namespace fusedk

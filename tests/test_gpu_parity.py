@@ -428,3 +428,17 @@ def test_cassi_index_offset_config4(sp, path):
     assert np.abs(xg - xo).max() <= _tol(path)
     assert np.abs(np.array(pag) - np.array(pao)).max() <= TOL_DB
     assert len(psg) == nband
+
+
+def test_fused_path_coverage(sp):
+    """Which configurations run the one-pass kernel (the rest use the exact kernels)."""
+    from scipnp import Solver
+    cases = [(dict(method="gap", C=8, T=5), True), (dict(method="gap", C=24, T=5), True),
+             (dict(method="admm", C=8, T=5), True), (dict(method="gap", C=28, T=5), True),
+             (dict(method="gap", C=8, T=3), True), (dict(method="gap", C=5, T=5), False),
+             (dict(method="gap", C=8, T=9), False), (dict(method="gap", C=40, T=5), False)]
+    for kw, want in cases:
+        with Solver(1, 32, 32, kw["C"], method=kw["method"], tv_iter_max=kw["T"]) as s:
+            assert s.uses_fused == want, kw
+    with Solver(1, 32, 32, 8, method="gap", fused=False) as s:
+        assert not s.uses_fused
