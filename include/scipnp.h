@@ -244,6 +244,9 @@ int scipnp_gap_denoise_host(const float *y, const float *Phi, const float *x0,
 int scipnp_admm_denoise_host(const float *y, const float *Phi, const float *x0,
                              const float *X_orig, const scipnp_params *p, int iters,
                              float *x_out, double *psnr_all, int *psnr_count);
+/* The two entries above keep their last solver handle (device buffers) for reuse by a call with
+ * identical parameters; this frees it.                                          */
+int scipnp_host_release(void);
 
 #ifdef __cplusplus
 }

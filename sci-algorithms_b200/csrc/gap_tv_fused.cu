@@ -10,9 +10,10 @@
 //   * a warp owns 32 consecutive pixels (lane = pixel) of one 4-channel chunk and
 //     walks down the rows of its segment; the K = C/4 chunk-warps of a pixel group
 //     sit in the same CTA because the projection couples the channels of a pixel;
-//   * rows are staged global -> shared with cp.async (16 B per request, coalesced
-//     on the global side, transposed to [chunk][pixel] on the shared side so that
-//     lane-per-pixel LDS.128 is conflict-free), double buffered, RB rows per block;
+//   * rows are staged global -> shared by the TMA unit (4-D tensor maps over
+//     [rows][W][C/4][4]: a box is RB rows x 32 pixels x one chunk, so the tiles arrive
+//     transposed to chunk-major and the lane-per-pixel LDS.128 is conflict-free; pixels
+//     outside the image are zero-filled), three-slot ring, one mbarrier per slot;
 //   * step rho: stage 0 turns row rho into f = x + lambda*s*Phi; stage i (1..R,
 //     R = tv_iter_max-1) advances dual iteration i on row rho-i using the row it
 //     kept from the previous step, so out_R(rho-R) leaves the pipeline every step.

@@ -641,22 +641,42 @@ int scipnp_solver_sync_error(scipnp_solver* s, int* timed_out, void* stream) {
     return SCIPNP_OK;
 }
 
+// The host-buffer entries keep their last solver handle: a second call with the same parameters
+// reuses its ~6 GB of device buffers instead of paying cudaMalloc/cudaFree again.
+static scipnp_solver* g_host_solver = nullptr;
+
 static int denoise_host(int method, const float* y, const float* Phi, const float* x0,
                         const float* X_orig, const scipnp_params* p, int iters, float* x_out,
                         double* psnr_all, int* psnr_count) {
     SCIPNP_REQUIRE(p && y && Phi && x_out, "null pointer");
     scipnp_params q = *p;
     q.method = method;
-    scipnp_solver* s = nullptr;
-    if (int e = scipnp_solver_create(&q, &s)) return e;
+    scipnp_solver* s = g_host_solver;
+    if (s && memcmp(&s->p, &q, sizeof(q)) != 0) {
+        scipnp_solver_destroy(s);
+        s = g_host_solver = nullptr;
+    }
+    if (!s) {
+        if (int e = scipnp_solver_create(&q, &s)) return e;
+        g_host_solver = s;
+    }
     int e = scipnp_solver_load(s, y, Phi, nullptr, x0, X_orig, nullptr);
     if (!e) e = scipnp_solver_run(s, iters, nullptr);
     if (!e) e = scipnp_solver_get_x(s, x_out, nullptr);
     int cnt = 0;
     if (!e) e = scipnp_solver_psnr(s, psnr_all, psnr_all ? iters * q.B : 0, &cnt, nullptr);
     if (psnr_count) *psnr_count = cnt;
-    scipnp_solver_destroy(s);
+    if (e) {                       // do not keep a handle in an unknown state
+        scipnp_solver_destroy(s);
+        g_host_solver = nullptr;
+    }
     return e;
+}
+
+int scipnp_host_release(void) {
+    if (g_host_solver) scipnp_solver_destroy(g_host_solver);
+    g_host_solver = nullptr;
+    return SCIPNP_OK;
 }
 
 int scipnp_gap_denoise_host(const float* y, const float* Phi, const float* x0, const float* X_orig,

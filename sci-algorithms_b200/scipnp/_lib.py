@@ -89,6 +89,7 @@ _SIGS = {
     "scipnp_solver_state": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "scipnp_solver_launch_count": (C.c_longlong, [_vp]),
     "scipnp_solver_uses_fused": (C.c_int, [_vp]),
+    "scipnp_host_release": (C.c_int, []),
     "scipnp_gap_denoise_host": (C.c_int, [_fp, _fp, _fp, _fp, C.POINTER(Params), _i, _fp,
                                           C.POINTER(C.c_double), C.POINTER(_i)]),
     "scipnp_admm_denoise_host": (C.c_int, [_fp, _fp, _fp, _fp, C.POINTER(Params), _i, _fp,
