@@ -442,3 +442,38 @@ def test_fused_path_coverage(sp):
             assert s.uses_fused == want, kw
     with Solver(1, 32, 32, 8, method="gap", fused=False) as s:
         assert not s.uses_fused
+
+
+@pytest.mark.parametrize("shape", [
+    # (B, H, W, C, tv_iter_max, method, accelerate, phi_batched)
+    (1, 37, 45, 8, 5, "gap", True, False),       # odd sizes: plane rows staged without TMA
+    (2, 3, 29, 4, 5, "gap", True, False),        # fewer rows than dual iterations
+    (1, 1, 64, 8, 5, "gap", False, False),       # a single row
+    (1, 50, 5, 12, 4, "gap", True, False),       # narrower than one pixel group, tv_iter_max 4
+    (3, 41, 70, 16, 3, "gap", True, True),       # per-measurement masks, tv_iter_max 3
+    (2, 33, 52, 28, 5, "admm", True, False),     # ADMM, 7 chunk-warps
+    (1, 130, 300, 32, 5, "admm", True, False),   # widest supported channel count
+    (5, 64, 64, 20, 5, "gap", True, False),      # more measurements than row bands
+])
+def test_fused_equals_exact_on_ragged_shapes(sp, shape):
+    """The one-pass kernel against the statement-order kernels on awkward shapes (image edges inside
+    a pixel group, segments shorter than the pipeline, batches, per-measurement masks)."""
+    import torch
+    from scipnp import Solver
+    B, H, W, C, T, method, acc, pb = shape
+    g = torch.Generator(device="cuda").manual_seed(H * 1000 + W)
+    Phi = (torch.rand((B, H, W, C) if pb else (H, W, C), device="cuda", generator=g) <= 0.5).float()
+    orig = torch.rand((B, H, W, C), device="cuda", generator=g)
+    y = (Phi * orig).sum(-1)
+    outs = []
+    for fused in (True, False):
+        with Solver(B, H, W, C, method=method, accelerate=acc, tv_weight=0.2, tv_iter_max=T,
+                    phi_batched=pb, fused=fused, gamma=0.02) as s:
+            assert s.uses_fused == fused
+            s.load(y, Phi, X_orig=orig)
+            s.run(5)
+            outs.append((s.get_x(), s.psnr_all()))
+    (xf, pf), (xe, pe) = outs
+    assert np.isfinite(xf).all()
+    assert np.abs(xf - xe).max() <= 2e-5
+    assert np.abs(pf - pe).max() <= 1e-3
