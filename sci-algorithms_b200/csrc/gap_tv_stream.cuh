@@ -521,11 +521,11 @@ int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream
         ctas_per_sm = n > 0 ? n : 1;
     }
     // One resident wave: every CTA takes an equal share of the (batch x bundle x row) units
-    // (see the kernel), but not less than 32 rows so that warm-up rows stay a small fraction.
+    // (see the kernel).  Large scenes fill all slots; small ones get segments of at least 8 rows.
     const long long slots = (long long)ctas_per_sm * num_sms();
     const long long nbundles = (fp.ngroups + fused_groups(K) - 1) / fused_groups(K);
     const long long total = (long long)fp.B * nbundles * fp.H;
-    long long n = total / 32;
+    long long n = total / 8;      // small scenes are latency-bound: short segments, more CTAs
     if (n > slots) n = slots;
     if (n < 1) n = 1;
     grid = dim3((unsigned)n, 1, 1);
