@@ -292,7 +292,7 @@ def run_ours(args):
         p = Params()
         p.method, p.accelerate, p.lambda_, p.gamma = 0, 1, 1.0, 0.0
         p.tv_weight, p.tv_eps, p.tv_iter_max, p.fused = TV_WEIGHT, 2e-4, TV_ITER, 1
-        p.B, p.H, p.W, p.C, p.phi_batched, p.halo_rows = 1, H, W, CR, 0, 0
+        p.B, p.H, p.W, p.C, p.phi_batched, p.clip01 = 1, H, W, CR, 0, 0
         n = C.c_int(0)
         solver.close()
         del solver

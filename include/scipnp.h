@@ -145,8 +145,8 @@ typedef struct scipnp_params {
     int   fused;         /* 1: one-pass fused iteration where available         */
     int   B, H, W, C;
     int   phi_batched;
-    int   halo_rows;     /* >0: this handle owns a row block of a taller scene;
-                            rows [0,halo) and [H-halo,H) are neighbour copies   */
+    int   clip01;        /* 1: clip the TV output to [0,1] every iteration, as the joint
+                            variant does (joint_pnp_sci_algo.py:633); 0 otherwise */
 } scipnp_params;
 
 int scipnp_solver_create(const scipnp_params *p, scipnp_solver **out);

@@ -19,7 +19,7 @@ import numpy as np
 from .tv_chambolle import denoise_tv_chambolle
 from .iqa import compare_psnr, compare_ssim
 
-__all__ = ["A_", "At_", "psnr", "phi_sum", "gap_denoise", "admm_denoise",
+__all__ = ["A_", "At_", "psnr", "phi_sum", "gap_denoise", "admm_denoise", "joint_admm_denoise",
            "admmdenoise_cacti", "gap_denoise_bayer", "cassi_shift_mask",
            "cassi_shift_cube"]
 
@@ -131,6 +131,36 @@ def admm_denoise(y, Phi_sum, A, At, _lambda=1, gamma=0.01, denoiser='tv',
             b = b - (x - theta)                       # :836
             if show_iqa and X_orig is not None:
                 psnr_all.append(psnr(X_orig, x))      # :840
+    ps, ss = _frame_iqa(X_orig, x)
+    return x, ps, ss, psnr_all
+
+
+def joint_admm_denoise(y, Phi_sum, A, At, _lambda=1, gamma=0.0, accelerate=None, denoiser='tv',
+                       iter_max=50, noise_estimate=False, sigma=None, tv_weight=0.1, tv_iter_max=5,
+                       multichannel=True, x0=None, model=None, X_orig=None, show_iqa=True,
+                       tvm='tv_chambolle'):
+    """ADMM-TV of the joint module (joint_pnp_sci_algo.py:502-665): as ``admm_denoise`` with
+    ``theta = np.clip(theta, 0, 1)`` after the denoiser (:633) and ``gamma`` defaulting to 0.
+    ``tvm`` 'ITV3D_FGP' and 'ITV2D_cham' also call denoise_tv_chambolle there (:608-611)."""
+    if denoiser.lower() != 'tv' or tvm not in ('tv_chambolle', 'ITV3D_FGP', 'ITV2D_cham'):
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    if x0 is None:
+        x0 = At(y)
+    sigma, iter_max = _as_schedule(sigma, iter_max)
+    x = x0
+    theta = x0
+    b = np.zeros_like(x0)
+    psnr_all = []
+    for idx, _ in enumerate(sigma):
+        for _it in range(iter_max[idx]):
+            yb = A(theta + b)                                             # :598
+            x = (theta + b) + _lambda * (At((y - yb) / (Phi_sum + gamma)))  # :599
+            theta = denoise_tv_chambolle(x - b, tv_weight, n_iter_max=tv_iter_max,
+                                         multichannel=multichannel)        # :607
+            theta = np.clip(theta, 0, 1)                                   # :633
+            b = b - (x - theta)                                            # :635
+            if show_iqa and X_orig is not None:
+                psnr_all.append(psnr(X_orig, x))
     ps, ss = _frame_iqa(X_orig, x)
     return x, ps, ss, psnr_all
 

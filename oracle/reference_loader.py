@@ -32,14 +32,15 @@ def available():
     return os.path.isfile(os.path.join(REFERENCE_PY, "pnp_sci_algo.py"))
 
 
-def load():
-    """Return ``(utils_module, pnp_sci_algo_module)`` of the reference."""
+def load(joint=False):
+    """Return ``(utils_module, pnp_sci_algo_module)`` of the reference; with ``joint=True`` the third
+    element is its ``joint_pnp_sci_algo`` module."""
     if not available():
         raise RuntimeError("reference tree not mounted at " + REFERENCE_PY)
     from . import tv_chambolle, iqa
 
     sys.dont_write_bytecode = True
-    saved = {k: sys.modules.get(k) for k in _STUBS + ["utils", "pnp_sci_algo"]}
+    saved = {k: sys.modules.get(k) for k in _STUBS + ["utils", "pnp_sci_algo", "joint_pnp_sci_algo"]}
     try:
         for name in _STUBS:
             m = types.ModuleType(name)
@@ -49,7 +50,7 @@ def load():
         sk.__version__ = "0.17.2"
         r = sys.modules["skimage.restoration"]
         r.denoise_tv_chambolle = tv_chambolle.denoise_tv_chambolle
-        for n in ("denoise_bilateral", "denoise_wavelet", "estimate_sigma"):
+        for n in ("denoise_bilateral", "denoise_wavelet", "estimate_sigma", "denoise_tv_bregman"):
             setattr(r, n, _absent(n))
         ms = sys.modules["skimage.measure"]
         ms.compare_psnr = iqa.compare_psnr
@@ -63,10 +64,11 @@ def load():
             .demosaicing_CFA_Bayer_Menon2007 = _absent("demosaicing")
         sys.path.insert(0, REFERENCE_PY)
         try:
-            for n in ("utils", "pnp_sci_algo"):
+            for n in ("utils", "pnp_sci_algo", "joint_pnp_sci_algo"):
                 sys.modules.pop(n, None)
             ref_utils = importlib.import_module("utils")
             ref_algo = importlib.import_module("pnp_sci_algo")
+            ref_joint = importlib.import_module("joint_pnp_sci_algo") if joint else None
         finally:
             sys.path.remove(REFERENCE_PY)
     finally:
@@ -75,6 +77,8 @@ def load():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+    if joint:
+        return ref_utils, ref_algo, ref_joint
     return ref_utils, ref_algo
 
 

@@ -172,7 +172,7 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     if (int e = make_frame_map(&maps.x, a.x_in, rows, a.W, a.C)) return e;
     if (cassi) maps.phi = maps.x;          // unused
     else if (int e = make_frame_map(&maps.phi, a.Phi, phi_rows, a.W, a.C)) return e;
-    const CassiParams cp{a.mask2d, a.cassi_step, a.mask_w, a.b_in, a.b_out, a.xproj_out, a.gamma};
+    const CassiParams cp{a.mask2d, a.cassi_step, a.mask_w, a.b_in, a.b_out, a.xproj_out, a.gamma, a.clip01};
     if (a.mode == MODE_ADMM && (!a.b_in || !a.b_out || !a.xproj_out || a.b_in == a.b_out || !aligned16(a.b_in))) {
         set_error("fused ADMM-TV needs distinct, aligned multiplier buffers and an x output");
         return SCIPNP_EINVAL;

@@ -31,6 +31,7 @@ struct CassiParams {
     const float* mask2d; int step, mask_w;
     // ADMM (MODE_ADMM): multiplier in/out, projection output x (returned by admm_denoise), gamma
     const float* b_in; float* b_out; float* xproj; float gamma;
+    int clip01;       // clip the TV output to [0,1] (joint_pnp_sci_algo.py:633)
 };
 
 // tensor maps of one launch: x_in and Phi as [rows][W][K][4 floats] (box RB x 32 x 1 x 4, i.e. the
@@ -433,8 +434,15 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     };
     // f_out = f(orow), the value that left the f delay line in this step: the ADMM multiplier update
     // b - (x - theta_new) equals theta_new - f  (pnp_sci_algo.py:836 with x = f + b)
-    auto store_row = [&](int orow, const P2 (&o)[2], const P2 (&f_out)[2]) {
+    auto store_row = [&](int orow, const P2 (&oo)[2], const P2 (&f_out)[2]) {
         if (own_px && orow >= r0 && orow < r1) {
+            P2 o[2] = {oo[0], oo[1]};
+            if constexpr (MODE == MODE_ADMM) {          // the joint ADMM variant clips theta
+                if (cp.clip01) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) { o[q].x = fminf(fmaxf(o[q].x, 0.f), 1.f); o[q].y = fminf(fmaxf(o[q].y, 0.f), 1.f); }
+                }
+            }
             *reinterpret_cast<float4*>(xo + ((size_t)orow * W + px) * C + 4 * k) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
             if constexpr (MODE == MODE_ADMM)
                 *reinterpret_cast<float4*>(cp.b_out + frame_b + ((size_t)orow * W + px) * C + 4 * k) =
@@ -510,7 +518,7 @@ int launch_stream_cassi_r4(int mode, int K, const FusedParams& fp, const FusedMa
                            dim3 grid, cudaStream_t st);
 
 template <int R, int MODE, int K, bool CASSI = false>
-int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream_t st, CassiParams cp = CassiParams{nullptr, 0, 0}) {
+int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream_t st, CassiParams cp = CassiParams{}) {
     auto kfn = gap_tv_stream_kernel<R, MODE, true, K, CASSI>;
     constexpr Smem L = smem_layout(K, fused_groups(K));
     static int ctas_per_sm = 0;            // resident CTAs of this instance, queried once
@@ -535,7 +543,7 @@ int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream
 
 template <int R, int MODE, bool CASSI = false>
 int launch_stream_mode(int K, const FusedParams& fp, const FusedMaps& maps, dim3 grid, cudaStream_t st,
-                       CassiParams cp = CassiParams{nullptr, 0, 0}) {
+                       CassiParams cp = CassiParams{}) {
     switch (K) {
 #ifndef SCIPNP_FUSED_FAST_BUILD
         case 1: return launch_stream_k<R, MODE, 1, CASSI>(fp, maps, grid, st, cp);

@@ -12,6 +12,7 @@ int launch_project(int mode, const float* a_in, const float* b_in, float* x_out,
                    const float* Phi_sum, float lambda, float gamma, int B, int H, int W, int C,
                    int phi_batched, cudaStream_t st);
 
+int launch_clip01(float* x, size_t n, cudaStream_t st);
 int launch_sq_err(const float* a, const float* b, size_t n_per_batch, int B, double* sums,
                   cudaStream_t st);
 
@@ -38,6 +39,7 @@ struct FusedArgs {
     bool workspace_clean;     // the energy accumulators are known to be zero (see launch_fused)
     // CASSI: Phi == nullptr and the coded aperture mask2d [H][mask_w] is read at offset step*c
     const float* mask2d; int cassi_step; int mask_w;
+    int clip01;               // clip the TV output to [0,1]
 };
 bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
 bool fused_cassi_supported(int mode, int B, int H, int W, int C, int tv_iter_max);

@@ -198,6 +198,13 @@ __global__ void admm_dual_kernel(float* __restrict__ b, const float* __restrict_
     for (; i < n; i += stride) b[i] = __fsub_rn(b[i], __fsub_rn(x[i], theta[i]));
 }
 
+// joint_pnp_sci_algo.py:633  theta = np.clip(theta, 0, 1)
+__global__ void clip01_kernel(float* __restrict__ x, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) x[i] = fminf(fmaxf(x[i], 0.f), 1.f);
+}
+
 // R10: sum of squared differences (double accumulation)
 __global__ void sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
                               double* __restrict__ out) {
@@ -303,6 +310,14 @@ int launch_project(int mode, const float* a_in, const float* b_in, float* x_out,
 #undef LAUNCH
     count_launch();
     return check_launch("project_kernel");
+}
+
+int launch_clip01(float* x, size_t n, cudaStream_t st) {
+    if (n == 0) return SCIPNP_OK;
+    unsigned grid = (unsigned)min((long long)ceil_div_ll((long long)n, 256 * 4), 8LL * num_sms());
+    clip01_kernel<<<grid, 256, 0, st>>>(x, n);
+    count_launch();
+    return check_launch("clip01_kernel");
 }
 
 int launch_sq_err(const float* a, const float* b, size_t n_per_batch, int B, double* sums,

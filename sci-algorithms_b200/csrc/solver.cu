@@ -112,7 +112,8 @@ int scipnp_solver_create(const scipnp_params* pp, scipnp_solver** out) {
     s->n_phisum = p.phi_batched ? s->n_meas : (size_t)p.H * p.W;
     s->n_phi = s->n_phisum * p.C;
     const int mode = p.method == 1 ? MODE_ADMM : (p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN);
-    s->use_fused = p.fused && fused_supported(mode, p.B, p.H, p.W, p.C, p.tv_iter_max);
+    s->use_fused = p.fused && fused_supported(mode, p.B, p.H, p.W, p.C, p.tv_iter_max) &&
+                   !(p.clip01 && p.method == 0);          // the fused kernel clips in ADMM mode only
     s->fused_possible = s->use_fused;
     DM(s->xa, s->n_frame, float);
     DM(s->xb, s->n_frame, float);
@@ -232,6 +233,7 @@ static int step_exact(scipnp_solver* s, int k, cudaStream_t st) {
         if (int e = tv_chambolle_exact(s->xa, s->xb, p.tv_weight, p.tv_eps, p.tv_iter_max, p.B, p.H, p.W,
                                        p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st)) return e;
         std::swap(s->xa, s->xb);
+        if (p.clip01) if (int e = launch_clip01(s->xa, s->n_frame, st)) return e;
         if (int e = record_sqerr(s, k, s->xa, st)) return e;
     } else {
         if (int e = launch_project(MODE_ADMM, s->xa, s->ba, s->xproj, s->fbuf, nullptr, nullptr, s->y,
@@ -239,6 +241,7 @@ static int step_exact(scipnp_solver* s, int k, cudaStream_t st) {
                                    p.phi_batched, st)) return e;
         if (int e = tv_chambolle_exact(s->fbuf, s->xa, p.tv_weight, p.tv_eps, p.tv_iter_max, p.B, p.H,
                                        p.W, p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st)) return e;
+        if (p.clip01) if (int e = launch_clip01(s->xa, s->n_frame, st)) return e;
         if (int e = scipnp_admm_dual_update(s->ba, s->xproj, s->xa, s->n_frame, st)) return e;
         if (int e = record_sqerr(s, k, s->xproj, st)) return e;
     }
@@ -256,6 +259,7 @@ static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
     a.B = p.B; a.H = p.H; a.W = p.W; a.C = p.C; a.phi_batched = p.phi_batched;
     a.workspace = s->fws; a.workspace_bytes = s->fws_bytes;
     a.flag = s->flags;
+    a.clip01 = p.clip01;
     a.workspace_clean = s->fws_clean;
     if (p.method == 0) {
         a.mode = p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN;

@@ -25,7 +25,7 @@ class Params(C.Structure):
         ("tv_weight", C.c_double), ("tv_eps", C.c_double),
         ("tv_iter_max", C.c_int), ("fused", C.c_int),
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
-        ("phi_batched", C.c_int), ("halo_rows", C.c_int),
+        ("phi_batched", C.c_int), ("clip01", C.c_int),
     ]
 
 

@@ -59,7 +59,7 @@ class Solver:
     """
 
     def __init__(self, B, H, W, C, method="gap", accelerate=True, _lambda=1.0, gamma=0.01,
-                 tv_weight=0.1, tv_iter_max=5, tv_eps=2.e-4, phi_batched=False, fused=True):
+                 tv_weight=0.1, tv_iter_max=5, tv_eps=2.e-4, phi_batched=False, fused=True, clip=False):
         require_device()
         self.shape = (int(B), int(H), int(W), int(C))
         self.method = METHOD_ADMM if str(method).lower() == "admm" else METHOD_GAP
@@ -74,7 +74,7 @@ class Solver:
         p.fused = 1 if fused else 0
         p.B, p.H, p.W, p.C = self.shape
         p.phi_batched = 1 if phi_batched else 0
-        p.halo_rows = 0
+        p.clip01 = 1 if clip else 0
         self.params = p
         h = ct.c_void_p()
         check(lib.scipnp_solver_create(ct.byref(p), ct.byref(h)))

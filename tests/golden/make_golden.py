@@ -33,7 +33,7 @@ def save(name, **arrs):
 
 
 def main():
-    ref_utils, ref_algo = reference_loader.load()
+    ref_utils, ref_algo, ref_joint = reference_loader.load(joint=True)
     f32 = np.float32
 
     # -- operators (R1, R2, R3, R10) -----------------------------------------
@@ -84,6 +84,12 @@ def main():
     save("admm", y=y, mask=mask, X_orig=Xo, x=x, psnr=np.array(ps),
          ssim=np.array(ss), psnr_all=np.array(pa), iter_max=12, tv_weight=0.3,
          tv_iter_max=5, _lambda=1.0, gamma=0.01)
+
+    # joint module's ADMM (clip of theta, gamma = 0 default): SURVEY 8f-1
+    x, ps, ss, pa = ref_joint.admm_denoise(y, ms, A, At, _lambda=1, gamma=0.0, denoiser='tv',
+                                           iter_max=12, tv_weight=0.3, tv_iter_max=5, X_orig=Xo)
+    save("joint_admm", y=y, mask=mask, X_orig=Xo, x=x, psnr=np.array(ps), ssim=np.array(ss),
+         psnr_all=np.array(pa), iter_max=12, tv_weight=0.3, tv_iter_max=5, _lambda=1.0, gamma=0.0)
 
     # warm start + ragged channel count (C=5, odd sizes)
     meas5, mask5, orig5 = cacti(33, 29, 5, 1, cfg=12)

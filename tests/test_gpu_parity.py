@@ -312,7 +312,7 @@ def test_c_abi_host_entry_matches_python_surface(sp, golden):
     p = Params()
     p.method, p.accelerate, p.lambda_, p.gamma = 0, 1, 1.0, 0.0
     p.tv_weight, p.tv_eps, p.tv_iter_max, p.fused = 0.3, 2e-4, 5, 0
-    p.B, p.H, p.W, p.C, p.phi_batched, p.halo_rows = 1, H, W, Cc, 0, 0
+    p.B, p.H, p.W, p.C, p.phi_batched, p.clip01 = 1, H, W, Cc, 0, 0
     y = np.ascontiguousarray(g["y"], np.float32)
     Phi = np.ascontiguousarray(g["mask"], np.float32)
     Xo = np.ascontiguousarray(g["X_orig"], np.float32)
@@ -477,3 +477,17 @@ def test_fused_equals_exact_on_ragged_shapes(sp, shape):
     assert np.isfinite(xf).all()
     assert np.abs(xf - xe).max() <= 2e-5
     assert np.abs(pf - pe).max() <= 1e-3
+
+
+def test_joint_admm_clip_golden(sp, golden, path):
+    """the joint module's ADMM-TV (theta clipped to [0,1], gamma = 0)."""
+    from scipnp import joint_pnp_sci_algo as J
+    g = golden("joint_admm")
+    A, At = _ops(g["mask"])
+    x, ps, ss, pa = J.admm_denoise(g["y"], _psum(g["mask"]), A, At, _lambda=1, gamma=0.0, denoiser='tv',
+                                   iter_max=12, tv_weight=0.3, tv_iter_max=5, X_orig=g["X_orig"],
+                                   tvm='ITV2D_cham')
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+    assert np.abs(np.array(ps) - g["psnr"]).max() <= TOL_DB
+    with pytest.raises(ValueError):
+        J.admm_denoise(g["y"], _psum(g["mask"]), A, At, denoiser='ffdnet', iter_max=1)

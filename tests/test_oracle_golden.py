@@ -135,3 +135,15 @@ def test_live_reference_matches_oracle():
     o = O.admm_denoise(y, ms, Ao, Ato, iter_max=7, tv_weight=0.2, tv_iter_max=5, X_orig=orig)
     np.testing.assert_array_equal(r[0], o[0])
     assert r[3] == o[3]
+
+
+def test_joint_admm_clip(golden):
+    """joint_pnp_sci_algo.admm_denoise (theta clipped to [0,1]) against the reference's joint module."""
+    g = golden("joint_admm")
+    A, At = _ops(g["mask"])
+    x, ps, ss, pa = O.joint_admm_denoise(g["y"], O.phi_sum(g["mask"]), A, At, _lambda=1, gamma=0.0,
+                                         denoiser='tv', iter_max=12, tv_weight=0.3, tv_iter_max=5,
+                                         X_orig=g["X_orig"])
+    np.testing.assert_array_equal(x, g["x"])
+    np.testing.assert_array_equal(np.array(pa), g["psnr_all"])
+    np.testing.assert_array_equal(np.array(ps), g["psnr"])
