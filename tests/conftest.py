@@ -12,6 +12,12 @@ for p in (ROOT, PKG):
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The shared library is a build artefact (git-ignored): build it on a fresh checkout so that the
+# CPU suite (symbol/ABI checks) can load it.  nvcc cross-compiles without a GPU.
+if not os.path.isfile(os.path.join(PKG, "scipnp", "libscipnp.so")):
+    import subprocess
+    subprocess.run(["bash", os.path.join(PKG, "build.sh")], check=True)
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
