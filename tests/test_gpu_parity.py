@@ -491,3 +491,54 @@ def test_joint_admm_clip_golden(sp, golden, path):
     assert np.abs(np.array(ps) - g["psnr"]).max() <= TOL_DB
     with pytest.raises(ValueError):
         J.admm_denoise(g["y"], _psum(g["mask"]), A, At, denoiser='ffdnet', iter_max=1)
+
+
+def test_c_abi_kernel_entries_directly(sp):
+    """The stateless C entries called with raw device pointers: one fused iteration equals
+    scipnp_gap_project + scipnp_tv_chambolle, and the ADMM pieces compose to the reference update."""
+    import ctypes as ct
+    import torch
+    from scipnp._lib import lib, check
+    B, H, W, Cc, T = 2, 48, 56, 8, 5
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Phi = (torch.rand((H, W, Cc), device="cuda", generator=g) <= 0.5).float()
+    x = torch.rand((B, H, W, Cc), device="cuda", generator=g)
+    y1 = 0.1 * torch.rand((B, H, W), device="cuda", generator=g)
+    y = torch.rand((B, H, W), device="cuda", generator=g) * Cc / 2
+    ps = Phi.sum(2)
+    ps[ps == 0] = 1
+    st = ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: ct.c_void_p(t.data_ptr())
+    # exact: projection then TV
+    xp, y1p = torch.empty_like(x), torch.empty_like(y1)
+    check(lib.scipnp_gap_project(ptr(x), ptr(xp), ptr(y1), ptr(y1p), ptr(y), ptr(Phi), ptr(ps), 1.0, 1,
+                                 B, H, W, Cc, 0, st))
+    ws = torch.empty(lib.scipnp_tv_workspace_bytes(B, H, W, Cc), dtype=torch.uint8, device="cuda")
+    xe = torch.empty_like(x)
+    check(lib.scipnp_tv_chambolle(ptr(xp), ptr(xe), 0.3, 2e-4, T, B, H, W, Cc, ptr(ws), ws.numel(),
+                                  None, None, 0, st))
+    # fused: one call
+    fws = torch.empty(max(256, lib.scipnp_gap_tv_workspace_bytes(B, H, W, Cc, T)), dtype=torch.uint8, device="cuda")
+    xf, y1f = torch.empty_like(x), torch.empty_like(y1)
+    flag = torch.zeros(4, dtype=torch.int32, device="cuda")
+    check(lib.scipnp_gap_tv_fused(ptr(x), ptr(xf), ptr(y1), ptr(y1f), ptr(y), ptr(Phi), ptr(ps), 1.0, 1,
+                                  0.3, 2e-4, T, B, H, W, Cc, 0, ptr(fws), fws.numel(), ptr(flag), st))
+    torch.cuda.synchronize()
+    assert int(flag[0]) == 0
+    assert float((xf - xe).abs().max()) <= 2e-5
+    assert float((y1f - y1p).abs().max()) <= 2e-5
+    # in == out is refused (ping-pong contract)
+    assert lib.scipnp_gap_tv_fused(ptr(x), ptr(x), ptr(y1), ptr(y1f), ptr(y), ptr(Phi), ptr(ps), 1.0, 1,
+                                   0.3, 2e-4, T, B, H, W, Cc, 0, ptr(fws), fws.numel(), None, st) == -1
+    # ADMM pieces: x = (theta+b) + At((y - A(theta+b))/(Phi_sum+gamma)); f = x - b; b -= x - theta
+    theta, b = x, 0.05 * torch.rand_like(x)
+    xo, fo = torch.empty_like(x), torch.empty_like(x)
+    check(lib.scipnp_admm_project(ptr(theta), ptr(b), ptr(xo), ptr(fo), ptr(y), ptr(Phi), ptr(ps), 1.0, 0.01,
+                                  B, H, W, Cc, 0, st))
+    u = theta + b
+    ref_x = u + ((y - (u * Phi).sum(-1)) / (ps + 0.01))[..., None] * Phi
+    assert float((xo - ref_x).abs().max()) <= 1e-5
+    assert float((fo - (ref_x - b)).abs().max()) <= 1e-5
+    b2 = b.clone()
+    check(lib.scipnp_admm_dual_update(ptr(b2), ptr(xo), ptr(theta), b2.numel(), st))
+    assert float((b2 - (b - (xo - theta))).abs().max()) <= 1e-6
