@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "internal.cuh"
 
 namespace scipnp {
@@ -84,10 +86,9 @@ struct Smem {
     int tile_bytes;          // all x (or all Phi) boxes of a slot: NG*K*BOX_BYTES
     int small_off;           // offset of the y/y1/Phi_sum rows inside a slot
     int buf_bytes;           // one slot
-    int part_off;            // partial dot products, two buffers of [RB][NG][32][KP]
+    int part_off;            // projection scale lambda*s per (row, pixel): two buffers of [RB][NG][32]
     int part_bytes;
     int bar_off;             // NSLOT mbarriers
-    int KP;
     int total;
 };
 __host__ __device__ constexpr Smem smem_layout(int K, int NG) {
@@ -95,9 +96,8 @@ __host__ __device__ constexpr Smem smem_layout(int K, int NG) {
     s.tile_bytes = NG * K * BOX_BYTES;
     s.small_off = 2 * s.tile_bytes;
     s.buf_bytes = s.small_off + 3 * NG * RB * 32 * 4;
-    s.KP = (K + 3) & ~3;
     s.part_off = NSLOT * s.buf_bytes;
-    s.part_bytes = RB * NG * 32 * s.KP * 4;
+    s.part_bytes = RB * NG * 32 * 4;
     s.bar_off = s.part_off + 2 * s.part_bytes;
     s.total = s.bar_off + 64;
     return s;
@@ -261,7 +261,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     const int load_end = min(H, rend);
     const int nblk = (rend - rs + RB - 1) / RB;
     // steps whose R stages all work on rows inside [r0, r1) and the image
-    const int fast_lo = r0 + R, fast_hi = min(r1, H - 1);
+    const int fast_lo = r0 + R, fast_hi = min(r1, H) - 1;
 
     const size_t frame_b = (size_t)b * H * W * C;        // batch offsets
     const size_t meas_b = (size_t)b * H * W;
@@ -284,10 +284,10 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
             if (tid == 0) {
                 const uint32_t bar = bar_base + slot * 8;
                 mbar_expect_tx(bar, kTileTx + (p.small_tma ? kSmallTx : 0u));
-#pragma unroll 1
+#pragma unroll
                 for (int g2 = 0; g2 < NG; ++g2) {
                     const int px0 = (group0 + g2) * OWN - R;
-#pragma unroll 1
+#pragma unroll
                     for (int kk = 0; kk < K; ++kk) {
                         const uint32_t d = dst + (g2 * K + kk) * BOX_BYTES;
                         tma_load_4d(d, &maps.x, 0, kk, px0, rowc0 + row0, bar);
@@ -326,9 +326,9 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     auto wait_block = [&](int blk) {       // tiles (and TMA-staged rows) of block blk have landed
         if (blk < nblk) mbar_wait(bar_base + ((gb + blk) % NSLOT) * 8, ((gb + blk) / NSLOT) & 1);
     };
-    // Phi of this thread's 4 channels at (row, px): from the staged tile, or -- CASSI -- the 2-D coded
+    // Phi of chunk kk (4 channels) at (row, gpx): from the staged tile, or -- CASSI -- the 2-D coded
     // aperture read at the per-band offset (the dispersion shift is an index offset, no stack in HBM)
-    auto load_phi = [&](const float4* tx, int row) -> float4 {
+    auto load_phi = [&](const float4* tx, int row, int gpx, bool in, int kk) -> float4 {
         if constexpr (!CASSI) {
             return tx[L.tile_bytes / 16];          // same slot layout as x, one tile further
         } else {
@@ -336,42 +336,61 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
             const float* mrow = cp.mask2d + ((size_t)(p.phi_batched ? b : 0) * H + min(row, H - 1)) * cp.mask_w;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int wm = px - cp.step * (4 * k + i);
-                v[i] = (px_in && row < H && wm >= 0 && wm < cp.mask_w) ? __ldg(mrow + wm) : 0.f;
+                const int wm = gpx - cp.step * (4 * kk + i);
+                v[i] = (in && row < H && wm >= 0 && wm < cp.mask_w) ? __ldg(mrow + wm) : 0.f;
             }
             return make_float4(v[0], v[1], v[2], v[3]);
         }
     };
-    // partial dot products of this warp's chunk for the rows of block `blk`
+    // Phase A of block `blk`: the Euclidean projection is pointwise in (row, px), so one thread per
+    // (row, pixel) of the block forms the whole dot product over the C channels from the staged
+    // tiles, updates y1 and leaves the scale lambda*s in shared memory for the K chunk-warps.
+    const float lam = p.lambda;
+    float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + meas_b : nullptr;
+    constexpr int NITEM = RB * NG * 32;
     auto phase_a = [&](int blk) {
         if (blk >= nblk) return;
         const unsigned char* buf = smem_raw + ((gb + blk) % NSLOT) * L.buf_bytes;
-        float* part = reinterpret_cast<float*>(smem_raw + L.part_off + ((gb + blk) & 1) * L.part_bytes);
-        float4 xv[RB], pv[RB];
+        float* sbuf = reinterpret_cast<float*>(smem_raw + L.part_off + ((gb + blk) & 1) * L.part_bytes);
 #pragma unroll
-        for (int j = 0; j < RB; ++j) {           // all loads first: one shared-memory round trip
-            const float4* tx = reinterpret_cast<const float4*>(buf + (gi * K + k) * BOX_BYTES) + j * 32 + lane;
-            xv[j] = tx[0];
-            pv[j] = load_phi(tx, rs + blk * RB + j);
-            if constexpr (MODE == MODE_ADMM) {          // the projection acts on u = theta + b
-                const int row = rs + blk * RB + j;
-                if (px_in && row < H) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(cp.b_in + frame_b + ((size_t)row * W + px) * C + 4 * k));
-                    xv[j].x += bv.x; xv[j].y += bv.y; xv[j].z += bv.z; xv[j].w += bv.w;
+        for (int it0 = 0; it0 < NITEM; it0 += NT) {
+            const int it = it0 + tid;                       // [j][g2][ln]
+            if (NITEM % NT != 0 && it >= NITEM) break;
+            const int ln = it & 31, g2 = (it >> 5) % NG, j = it / (32 * NG);
+            const int row = rs + blk * RB + j;
+            const int gpx = (group0 + g2) * OWN - R + ln;
+            const bool in = (group0 + g2) < p.ngroups && gpx >= 0 && gpx < W;
+            const float4* tx = reinterpret_cast<const float4*>(buf + g2 * K * BOX_BYTES) + j * 32 + ln;
+            float acc = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                float4 xv = tx[kk * (BOX_BYTES / 16)];
+                const float4 pv = load_phi(tx + kk * (BOX_BYTES / 16), row, gpx, in, kk);
+                if constexpr (MODE == MODE_ADMM) {          // the projection acts on u = theta + b
+                    if (in && row < H) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(cp.b_in + frame_b + ((size_t)row * W + gpx) * C + 4 * kk));
+                        xv.x += bv.x; xv.y += bv.y; xv.z += bv.z; xv.w += bv.w;
+                    }
                 }
+                acc = fmaf(xv.x, pv.x, acc);
+                acc = fmaf(xv.y, pv.y, acc);
+                acc = fmaf(xv.z, pv.z, acc);
+                acc = fmaf(xv.w, pv.w, acc);
             }
-        }
-#pragma unroll
-        for (int j = 0; j < RB; ++j) {
-            float d = xv[j].x * pv[j].x;
-            d = fmaf(xv[j].y, pv[j].y, d);
-            d = fmaf(xv[j].z, pv[j].z, d);
-            d = fmaf(xv[j].w, pv[j].w, d);
-            part[((j * NG + gi) * 32 + lane) * L.KP + k] = d;
-            if (k == 0) {
-#pragma unroll
-                for (int kk = K; kk < L.KP; ++kk) part[((j * NG + gi) * 32 + lane) * L.KP + kk] = 0.f;
+            const float* sm = reinterpret_cast<const float*>(buf + L.small_off) + (g2 * RB + j) * 32 + ln;
+            const float yv = sm[0];
+            const float psv = sm[2 * NG * RB * 32];
+            float sv;
+            if (MODE == MODE_GAP_ACC) {
+                const float y1n = sm[NG * RB * 32] + (yv - acc);
+                if (in && ln >= R && ln < 32 - R && row >= r0 && row < r1) y1o[(size_t)row * W + gpx] = y1n;
+                sv = (y1n - acc) * fast_rcp(psv);
+            } else if (MODE == MODE_ADMM) {
+                sv = (yv - acc) * fast_rcp(psv + cp.gamma);      // pnp_sci_algo.py:809
+            } else {
+                sv = (yv - acc) * fast_rcp(psv);
             }
+            sbuf[it] = in ? sv * lam : 0.f;
         }
     };
 
@@ -394,38 +413,25 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     // (and of any lane outside the image, whose state then stays identically zero)
     sc.src_right = (px_in && px < W - 1 && lane < 31) ? lane + 1 : lane;
     sc.rs = rs; sc.r0 = r0; sc.r1 = r1; sc.H = H;
-    const float lam = p.lambda;
-    float* xo = p.x_out + frame_b;
-    float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + meas_b : nullptr;
+    // Output cursors of this thread: element offsets of (row 0, px, channel 4k) in a frame and of
+    // (row 0, px) in a measurement plane.  Rows are added per block (FAST: once per RB rows), so the
+    // steady state carries no 64-bit multiplies.  Never dereferenced for pixels outside the image.
+    const long long xstride = (long long)W * C;
+    const long long xoff0 = (long long)frame_b + (long long)px * C + 4 * k;
 
-    // stage 0 of step rho (row j of the block in `buf`): Euclidean projection -> f(rho)
-    auto project_row = [&](const unsigned char* buf, const float* part, int j, int rho, P2 (&f_new)[2]) {
+    // stage 0 of step rho (row j of the block in `buf`): f(rho) = x + (lambda*s) * Phi for this warp's chunk
+    // ROWS_OK: the caller guarantees r0 <= rho < r1 (no row predicate on the stores)
+    auto project_row = [&](const unsigned char* buf, const float* sbuf, int j, int rho, long long xoff, auto rows_ok, P2 (&f_new)[2]) {
+        constexpr bool ROWS_OK = decltype(rows_ok)::value;
         const float4* tx = reinterpret_cast<const float4*>(buf + (gi * K + k) * BOX_BYTES) + j * 32 + lane;
-        const float4 xv = tx[0], pv = load_phi(tx, rho);
-        const float4* pp = reinterpret_cast<const float4*>(part + ((j * NG + gi) * 32 + lane) * L.KP);
-        float yb = 0.f;
-#pragma unroll
-        for (int q = 0; q < L.KP / 4; ++q) { const float4 t = pp[q]; yb += (t.x + t.y) + (t.z + t.w); }
-        const float* sm = reinterpret_cast<const float*>(buf + L.small_off) + (gi * RB + j) * 32 + lane;
-        const float yv = sm[0];
-        const float psv = sm[2 * NG * RB * 32];
-        float s;
-        if (MODE == MODE_GAP_ACC) {
-            const float y1n = sm[NG * RB * 32] + (yv - yb);
-            if (k == 0 && own_px && rho >= r0 && rho < r1) y1o[(size_t)rho * W + px] = y1n;
-            s = __fdividef(y1n - yb, psv);
-        } else if (MODE == MODE_ADMM) {
-            s = __fdividef(yv - yb, psv + cp.gamma);      // pnp_sci_algo.py:809
-        } else {
-            s = __fdividef(yv - yb, psv);
-        }
-        const P2 s2 = splat(px_in ? s * lam : 0.f);
+        const float4 xv = tx[0], pv = load_phi(tx, rho, px, px_in, k);
+        const P2 s2 = splat(sbuf[(j * NG + gi) * 32 + lane]);
         f_new[0] = fma2(s2, make_float2(pv.x, pv.y), make_float2(xv.x, xv.y));
         f_new[1] = fma2(s2, make_float2(pv.z, pv.w), make_float2(xv.z, xv.w));
         if constexpr (MODE == MODE_ADMM) {
             // f = x - b = theta + lambda*s*Phi is the TV input; x = f + b is what admm_denoise returns
-            if (own_px && rho >= r0 && rho < r1) {
-                const size_t o = frame_b + ((size_t)rho * W + px) * C + 4 * k;
+            if (own_px && (ROWS_OK || (rho >= r0 && rho < r1))) {
+                const long long o = xoff;
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(cp.b_in + o));
                 *reinterpret_cast<float4*>(cp.xproj + o) =
                     make_float4(f_new[0].x + bv.x, f_new[0].y + bv.y, f_new[1].x + bv.z, f_new[1].y + bv.w);
@@ -434,8 +440,9 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     };
     // f_out = f(orow), the value that left the f delay line in this step: the ADMM multiplier update
     // b - (x - theta_new) equals theta_new - f  (pnp_sci_algo.py:836 with x = f + b)
-    auto store_row = [&](int orow, const P2 (&oo)[2], const P2 (&f_out)[2]) {
-        if (own_px && orow >= r0 && orow < r1) {
+    auto store_row = [&](int orow, long long xoff, auto rows_ok, const P2 (&oo)[2], const P2 (&f_out)[2]) {
+        constexpr bool ROWS_OK = decltype(rows_ok)::value;
+        if (own_px && (ROWS_OK || (orow >= r0 && orow < r1))) {
             P2 o[2] = {oo[0], oo[1]};
             if constexpr (MODE == MODE_ADMM) {          // the joint ADMM variant clips theta
                 if (cp.clip01) {
@@ -443,9 +450,9 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
                     for (int q = 0; q < 2; ++q) { o[q].x = fminf(fmaxf(o[q].x, 0.f), 1.f); o[q].y = fminf(fmaxf(o[q].y, 0.f), 1.f); }
                 }
             }
-            *reinterpret_cast<float4*>(xo + ((size_t)orow * W + px) * C + 4 * k) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+            *reinterpret_cast<float4*>(p.x_out + xoff) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
             if constexpr (MODE == MODE_ADMM)
-                *reinterpret_cast<float4*>(cp.b_out + frame_b + ((size_t)orow * W + px) * C + 4 * k) =
+                *reinterpret_cast<float4*>(cp.b_out + xoff) =
                     make_float4(o[0].x - f_out[0].x, o[0].y - f_out[0].y, o[1].x - f_out[1].x, o[1].y - f_out[1].y);
         }
     };
@@ -453,10 +460,11 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     issue(0);
     issue(1);
     wait_block(0);
+    if (!p.small_tma) { cp_async_wait<0>(); __syncthreads(); }   // phase A reads the y / y1 / Phi_sum rows
     phase_a(0);
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
-        // one barrier per block: block blk+1 has landed, the partials of block blk are visible,
+        // one barrier per block: block blk+1 has landed, the projection scales of block blk are visible,
         // and everybody is done with slot (blk+2)%3 (last read in the previous iteration)
         if (!p.small_tma) cp_async_wait<0>();
         __syncthreads();
@@ -464,17 +472,19 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         wait_block(blk + 1);
         phase_a(blk + 1);
         const unsigned char* buf = smem_raw + ((gb + blk) % NSLOT) * L.buf_bytes;
-        const float* part = reinterpret_cast<const float*>(smem_raw + L.part_off + ((gb + blk) & 1) * L.part_bytes);
+        const float* sbuf = reinterpret_cast<const float*>(smem_raw + L.part_off + ((gb + blk) & 1) * L.part_bytes);
         const int rho0 = rs + blk * RB;
+        const long long xoff_in = xoff0 + (long long)rho0 * xstride;      // (rho0, px, 4k)
+        const long long xoff_out = xoff_in - R * xstride;                  // (rho0 - R, px, 4k)
         if (rho0 >= fast_lo && rho0 + RB - 1 <= fast_hi) {
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
                 const int rho = rho0 + j;
                 P2 f_new[2], o_new[2];
-                project_row(buf, part, j, rho, f_new);
+                project_row(buf, sbuf, j, rho, xoff_in + j * xstride, std::true_type{}, f_new);
                 const P2 f_out[2] = {S.fd[R - 1][0], S.fd[R - 1][1]};
                 pipe_step<R, CHECK, true>(S, sc, rho, f_new, o_new);
-                store_row(rho - R, o_new, f_out);
+                store_row(rho - R, xoff_out + j * xstride, std::true_type{}, o_new, f_out);
             }
         } else {
 #pragma unroll 1
@@ -482,10 +492,10 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
                 const int rho = rho0 + j;
                 if (rho < rend) {
                     P2 f_new[2] = {zero2, zero2}, o_new[2];
-                    if (rho < H) project_row(buf, part, j, rho, f_new);
+                    if (rho < H) project_row(buf, sbuf, j, rho, xoff_in + j * xstride, std::false_type{}, f_new);
                     const P2 f_out[2] = {S.fd[R - 1][0], S.fd[R - 1][1]};
                     pipe_step<R, CHECK, false>(S, sc, rho, f_new, o_new);
-                    store_row(rho - R, o_new, f_out);
+                    store_row(rho - R, xoff_out + j * xstride, std::false_type{}, o_new, f_out);
                 }
             }
         }
