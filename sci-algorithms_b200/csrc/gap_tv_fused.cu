@@ -73,15 +73,15 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// frame stack [rows][W][K][4 floats] -> boxes of RB rows x 32 pixels x 1 chunk x 4 floats
+// frame stack [rows][W][C] -> boxes of RB rows x 32 pixels x 4*SUBK channels (fused_subk)
 int make_frame_map(CUtensorMap* tm, const float* base, long long rows, int W, int C) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SCIPNP_ECUDA; }
-    cuuint64_t dims[4] = {4, (cuuint64_t)(C / 4), (cuuint64_t)W, (cuuint64_t)rows};
-    cuuint64_t strides[3] = {16, (cuuint64_t)C * 4, (cuuint64_t)W * C * 4};
-    cuuint32_t box[4] = {4, 1, 32, (cuuint32_t)RB};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es,
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)rows};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4};
+    cuuint32_t box[3] = {(cuuint32_t)(4 * fused_subk(C / 4)), 32, (cuuint32_t)RB};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(frame) failed with CUresult %d", (int)r); return SCIPNP_ECUDA; }

@@ -11,8 +11,15 @@ namespace scipnp {
 namespace fusedk {
 
 constexpr int RB = 4;             // rows per staged block
-constexpr int NSLOT = 3;          // staging ring: block b in slot b % 3
-constexpr int BOX_BYTES = RB * 32 * 16;   // one TMA box: RB rows x 32 pixels x one 4-channel chunk
+constexpr int BOX_BYTES = RB * 32 * 16;   // RB rows x 32 pixels x one 4-channel chunk
+// A TMA box of a frame tile is RB rows x 32 pixels x SUBK chunks, pixel-major in shared memory.
+// SUBK = K moves whole pixels: a box row is then one contiguous 32*C*4-byte piece of global memory,
+// which is what the TMA unit is fast at (measured on the config-5 scene, loads + stores only:
+// 0.54 ms per pass against 0.68 ms with 16-byte pieces; 48-byte pieces are no better than 16).
+// The price is the bank pattern of the lane-per-pixel LDS.128: conflict-free for odd K, two-way
+// for K = 2, 6 (phase A avoids it by swapping chunk pairs on every other group of four lanes),
+// worse for K = 4, 8 -- those keep one box per chunk (SUBK = 1, chunk-major, conflict-free).
+__host__ __device__ constexpr int fused_subk(int K) { return (K & 3) == 0 ? 1 : K; }
 constexpr int kMaxWarps = 8;
 
 struct FusedParams {
@@ -36,8 +43,8 @@ struct CassiParams {
     int clip01;       // clip the TV output to [0,1] (joint_pnp_sci_algo.py:633)
 };
 
-// tensor maps of one launch: x_in and Phi as [rows][W][K][4 floats] (box RB x 32 x 1 x 4, i.e. the
-// transposition to chunk-major tiles is done by the TMA unit), y / y1_in / Phi_sum as [rows][W]
+// tensor maps of one launch: x_in and Phi as [rows][W][C] (box RB x 32 x 4*SUBK), y / y1_in / Phi_sum
+// as [rows][W]
 struct FusedMaps { CUtensorMap x, phi, y, y1, ps; };
 
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
@@ -53,6 +60,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -64,10 +74,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
-        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
     asm volatile(
@@ -79,8 +89,8 @@ __device__ __forceinline__ float fast_sqrt(float v) { float r; asm("sqrt.approx.
 __device__ __forceinline__ float fast_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 
 // shared-memory carve-up (per CTA), all offsets in bytes.  One staging slot holds RB rows:
-//   x   tiles [NG][K][RB][32] float4   (one TMA box per (group, chunk))
-//   Phi tiles [NG][K][RB][32] float4
+//   x   tiles [NG][K/SUBK][RB][32][SUBK] float4   (one TMA box per (group, sub-box))
+//   Phi tiles likewise
 //   y, y1, Phi_sum  [3][NG][RB][32] float
 struct Smem {
     int tile_bytes;          // all x (or all Phi) boxes of a slot: NG*K*BOX_BYTES
@@ -88,17 +98,29 @@ struct Smem {
     int buf_bytes;           // one slot
     int part_off;            // projection scale lambda*s per (row, pixel): two buffers of [RB][NG][32]
     int part_bytes;
-    int bar_off;             // NSLOT mbarriers
+    int bar_off;             // nslot TMA mbarriers + the phase-A mbarrier
+    int nslot, nsbuf;        // staging ring depth; buffers of the scale plane
     int total;
 };
+// Ring depth.  With four slots (and three scale planes) the per-block CTA barrier becomes a split
+// arrive/wait on an mbarrier: a warp may then run up to one block ahead of the slowest one.  Used
+// when two CTAs with four slots still fit one SM (228 KB, 1 KB reserved per CTA); else three slots
+// and a plain __syncthreads per block.
+__host__ __device__ constexpr int fused_slots(int K, int NG) {
+    const int buf = 2 * NG * K * BOX_BYTES + 3 * NG * RB * 32 * 4;
+    const int ctas = NG * K > 6 ? 1 : 2;       // fused_ctas(K), defined below
+    return ctas * (4 * buf + 3 * RB * NG * 32 * 4 + 64 + 1024) <= 232448 ? 4 : 3;
+}
 __host__ __device__ constexpr Smem smem_layout(int K, int NG) {
     Smem s{};
+    s.nslot = fused_slots(K, NG);
+    s.nsbuf = s.nslot - 1;
     s.tile_bytes = NG * K * BOX_BYTES;
     s.small_off = 2 * s.tile_bytes;
     s.buf_bytes = s.small_off + 3 * NG * RB * 32 * 4;
-    s.part_off = NSLOT * s.buf_bytes;
+    s.part_off = s.nslot * s.buf_bytes;
     s.part_bytes = RB * NG * 32 * 4;
-    s.bar_off = s.part_off + 2 * s.part_bytes;
+    s.bar_off = s.part_off + s.nsbuf * s.part_bytes;
     s.total = s.bar_off + 64;
     return s;
 }
@@ -122,6 +144,10 @@ __device__ __forceinline__ P2 shfl_up2(P2 a) {
 // staging per CTA so that two CTAs share an SM)
 __host__ __device__ constexpr int fused_groups(int K) { return 6 / K < 1 ? 1 : 6 / K; }
 __host__ __device__ constexpr int fused_threads(int K) { return fused_groups(K) * K * 32; }
+// resident CTAs per SM the kernel is compiled for: two CTAs of <= 6 warps (168 registers per
+// thread); the 7- and 8-warp CTAs of C = 28, 32 would be squeezed to 128 registers and spill, so
+// they get the whole register file and run one per SM
+__host__ __device__ constexpr int fused_ctas(int K) { return fused_threads(K) > 192 ? 1 : 2; }
 
 // Register state of one thread: 4 channels as two packed pairs, R pipeline stages.
 template <int R>
@@ -212,11 +238,19 @@ __device__ __forceinline__ void pipe_step(Pipe<R>& S, const StepConst& c, int rh
 }
 
 template <int R, int MODE, bool CHECK, int K, bool CASSI>
-__global__ void __launch_bounds__(fused_threads(K), 2)
+__global__ void __launch_bounds__(fused_threads(K), fused_ctas(K))
 gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps, const CassiParams cp) {
     constexpr int NG = fused_groups(K);
     constexpr int NT = fused_threads(K);
     constexpr Smem L = smem_layout(K, NG);
+    constexpr int NSLOT = L.nslot, NSBUF = L.nsbuf;
+    constexpr bool SPLIT = NSLOT == 4;           // split per-block barrier (see fused_slots)
+    constexpr int SUBK = fused_subk(K), NSUB = K / SUBK;
+    constexpr bool SWAP = SUBK > 1 && (SUBK & 1) == 0;    // phase A: chunk pairs swapped on lanes 4..7 of each 8
+    // float4 index of chunk kk of (group g2, row j, pixel ln) inside a frame tile
+    auto chunk_idx = [](int g2, int kk, int j, int ln) {
+        return (((g2 * NSUB + kk / SUBK) * RB + j) * 32 + ln) * SUBK + kk % SUBK;
+    };
     constexpr int OWN = 32 - 2 * R;              // owned pixels per group
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = p.W, H = p.H, C = p.C;
@@ -228,6 +262,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < NSLOT; ++i) mbar_init(bar_base + i * 8, 1);
+        mbar_init(bar_base + NSLOT * 8, NT / 32);          // phase A done: one arrival per warp
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
@@ -243,6 +278,10 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     long long unit = (long long)blockIdx.x * per_cta;
     const long long unit_end = min(total, unit + per_cta);
     int gb = 0;                                  // running block counter: ring slot and mbarrier phase
+    const uint32_t pa_bar = bar_base + NSLOT * 8;
+    uint32_t pa_ctr = 0;                         // completed phase-A waits (parity of pa_bar)
+    // the y / y1 / Phi_sum rows staged by cp.async need the full barrier for visibility
+    const bool split = SPLIT && p.small_tma;
 #pragma unroll 1
     while (unit < unit_end) {
     const int strip = (int)(unit / H);
@@ -276,22 +315,28 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     const int phirow0 = p.phi_batched ? b * H : 0;
     // cp.async fallback for the y / y1 / Phi_sum rows when W % 4 != 0 (TMA needs 16-byte row pitch)
     constexpr int NSMALL = (3 * NG * RB * 32 + NT - 1) / NT;
-    auto issue = [&](int blk) {
+    // Per-block duties rotate over the warps (virtual warp index vw = warp - rot mod NW): the first
+    // NITEM/32 virtual warps run phase A, the last one programs the TMA unit.  With the split
+    // barrier the warps may drift by a block, so the extra work averages out instead of making
+    // one warp the pace setter.
+    constexpr int NW = NT / 32;
+    auto vwarp = [&](int rot) { const int v = warp - rot; return v < 0 ? v + NW : v; };
+    auto issue = [&](int blk, int rot) {
         if (blk < nblk) {
             const int slot = (gb + blk) % NSLOT;
             const uint32_t dst = smem_base + slot * L.buf_bytes;
             const int row0 = rs + blk * RB;
-            if (tid == 0) {
+            if (lane == 0 && vwarp(rot) == NW - 1) {
                 const uint32_t bar = bar_base + slot * 8;
                 mbar_expect_tx(bar, kTileTx + (p.small_tma ? kSmallTx : 0u));
 #pragma unroll
                 for (int g2 = 0; g2 < NG; ++g2) {
                     const int px0 = (group0 + g2) * OWN - R;
 #pragma unroll
-                    for (int kk = 0; kk < K; ++kk) {
-                        const uint32_t d = dst + (g2 * K + kk) * BOX_BYTES;
-                        tma_load_4d(d, &maps.x, 0, kk, px0, rowc0 + row0, bar);
-                        if constexpr (!CASSI) tma_load_4d(d + L.tile_bytes, &maps.phi, 0, kk, px0, phirow0 + row0, bar);
+                    for (int sb = 0; sb < NSUB; ++sb) {
+                        const uint32_t d = dst + (g2 * NSUB + sb) * SUBK * BOX_BYTES;
+                        tma_load_3d(d, &maps.x, 4 * SUBK * sb, px0, rowc0 + row0, bar);
+                        if constexpr (!CASSI) tma_load_3d(d + L.tile_bytes, &maps.phi, 4 * SUBK * sb, px0, phirow0 + row0, bar);
                     }
                     if (p.small_tma) {
                         const uint32_t ds = dst + L.small_off + g2 * RB * 128;
@@ -348,24 +393,29 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     const float lam = p.lambda;
     float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + meas_b : nullptr;
     constexpr int NITEM = RB * NG * 32;
-    auto phase_a = [&](int blk) {
+    auto phase_a = [&](int blk, int rot) {
         if (blk >= nblk) return;
+        const int vtid = vwarp(rot) * 32 + lane;
         const unsigned char* buf = smem_raw + ((gb + blk) % NSLOT) * L.buf_bytes;
-        float* sbuf = reinterpret_cast<float*>(smem_raw + L.part_off + ((gb + blk) & 1) * L.part_bytes);
+        float* sbuf = reinterpret_cast<float*>(smem_raw + L.part_off + ((gb + blk) % NSBUF) * L.part_bytes);
 #pragma unroll
         for (int it0 = 0; it0 < NITEM; it0 += NT) {
-            const int it = it0 + tid;                       // [j][g2][ln]
+            const int it = it0 + vtid;                      // [j][g2][ln]
             if (NITEM % NT != 0 && it >= NITEM) break;
             const int ln = it & 31, g2 = (it >> 5) % NG, j = it / (32 * NG);
             const int row = rs + blk * RB + j;
             const int gpx = (group0 + g2) * OWN - R + ln;
             const bool in = (group0 + g2) < p.ngroups && gpx >= 0 && gpx < W;
-            const float4* tx = reinterpret_cast<const float4*>(buf + g2 * K * BOX_BYTES) + j * 32 + ln;
+            const float4* tile = reinterpret_cast<const float4*>(buf);
+            // SWAP: this lane visits the chunks as 1,0,3,2,.. so that a quarter-warp touches 8 bank groups
+            const int sw = SWAP ? (ln >> 2) & 1 : 0;
             float acc = 0.f;
 #pragma unroll
-            for (int kk = 0; kk < K; ++kk) {
-                float4 xv = tx[kk * (BOX_BYTES / 16)];
-                const float4 pv = load_phi(tx + kk * (BOX_BYTES / 16), row, gpx, in, kk);
+            for (int k0 = 0; k0 < K; ++k0) {
+                const int kk = SWAP ? k0 + ((k0 & 1) ? -sw : sw) : k0;
+                const float4* tx = tile + chunk_idx(g2, k0, j, ln) + (kk - k0);
+                float4 xv = tx[0];
+                const float4 pv = load_phi(tx, row, gpx, in, kk);
                 if constexpr (MODE == MODE_ADMM) {          // the projection acts on u = theta + b
                     if (in && row < H) {
                         const float4 bv = __ldg(reinterpret_cast<const float4*>(cp.b_in + frame_b + ((size_t)row * W + gpx) * C + 4 * kk));
@@ -423,7 +473,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     // ROWS_OK: the caller guarantees r0 <= rho < r1 (no row predicate on the stores)
     auto project_row = [&](const unsigned char* buf, const float* sbuf, int j, int rho, long long xoff, auto rows_ok, P2 (&f_new)[2]) {
         constexpr bool ROWS_OK = decltype(rows_ok)::value;
-        const float4* tx = reinterpret_cast<const float4*>(buf + (gi * K + k) * BOX_BYTES) + j * 32 + lane;
+        const float4* tx = reinterpret_cast<const float4*>(buf) + chunk_idx(gi, k, j, lane);
         const float4 xv = tx[0], pv = load_phi(tx, rho, px, px_in, k);
         const P2 s2 = splat(sbuf[(j * NG + gi) * 32 + lane]);
         f_new[0] = fma2(s2, make_float2(pv.x, pv.y), make_float2(xv.x, xv.y));
@@ -457,22 +507,39 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         }
     };
 
-    issue(0);
-    issue(1);
+    // phase A of a block is done (scale plane written) by this warp: one arrival per warp
+    auto pa_arrive = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pa_bar);
+    };
+    int rot = gb % NW;
+    issue(0, rot);
+    issue(1, rot);
     wait_block(0);
     if (!p.small_tma) { cp_async_wait<0>(); __syncthreads(); }   // phase A reads the y / y1 / Phi_sum rows
-    phase_a(0);
+    phase_a(0, rot);
+    if (split) pa_arrive();
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
-        // one barrier per block: block blk+1 has landed, the projection scales of block blk are visible,
-        // and everybody is done with slot (blk+2)%3 (last read in the previous iteration)
-        if (!p.small_tma) cp_async_wait<0>();
-        __syncthreads();
-        issue(blk + 2);
+        // Once per block: the scale plane of block blk is complete.  Split form: every warp arrived
+        // after its phase A of block blk, i.e. before it started the rows of block blk-1, so passing
+        // the wait also means everybody is done with block blk-2 -- whose slot (of four) the next TMA
+        // loads overwrite and whose scale plane (of three) phase A of block blk+1 overwrites.
+        // Barrier form (three slots): everybody is done with block blk-1.
+        if (split) {
+            mbar_wait(pa_bar, pa_ctr & 1);
+            ++pa_ctr;
+        } else {
+            if (!p.small_tma) cp_async_wait<0>();
+            __syncthreads();
+        }
+        rot = rot + 1 == NW ? 0 : rot + 1;
+        issue(blk + 2, rot);
         wait_block(blk + 1);
-        phase_a(blk + 1);
+        phase_a(blk + 1, rot);
+        if (split && blk + 1 < nblk) pa_arrive();
         const unsigned char* buf = smem_raw + ((gb + blk) % NSLOT) * L.buf_bytes;
-        const float* sbuf = reinterpret_cast<const float*>(smem_raw + L.part_off + ((gb + blk) & 1) * L.part_bytes);
+        const float* sbuf = reinterpret_cast<const float*>(smem_raw + L.part_off + ((gb + blk) % NSBUF) * L.part_bytes);
         const int rho0 = rs + blk * RB;
         const long long xoff_in = xoff0 + (long long)rho0 * xstride;      // (rho0, px, 4k)
         const long long xoff_out = xoff_in - R * xstride;                  // (rho0 - R, px, 4k)
