@@ -460,7 +460,10 @@ struct PullJob {
     int epoch;
 };
 
-__global__ void __launch_bounds__(256) tile_exchange_kernel(const PullJob j) {
+// Peer loads over NVLink are latency-bound (a round trip is a few microseconds), so the pull wants as
+// many loads in flight as the GPU can hold: full-size CTAs, two per SM, about one float4 per thread.
+constexpr int kPullThreads = 1024;
+__global__ void __launch_bounds__(kPullThreads, 2) tile_exchange_kernel(const PullJob j) {
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
             __threadfence_system();
@@ -476,11 +479,18 @@ __global__ void __launch_bounds__(256) tile_exchange_kernel(const PullJob j) {
     }
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
+    long long nmax = 0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const float4* __restrict__ s = j.src[r];
-        float4* __restrict__ d = j.dst[r];
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < j.n4[r]; i += stride) d[i] = s[i];
+    for (int r = 0; r < 4; ++r) nmax = j.n4[r] > nmax ? j.n4[r] : nmax;
+    // all four regions per pass, loads first: one NVLink round trip per pass instead of four
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nmax; i += stride) {
+        float4 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (i < j.n4[r]) v[r] = j.src[r][i];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (i < j.n4[r]) j.dst[r][i] = v[r];
     }
     __threadfence();
     __syncthreads();
@@ -608,10 +618,10 @@ int scipnp_solver_exchange(scipnp_solver* s, void* stream) {
     j.counter = s->sync + 5;
     j.timeout_flag = s->sync + 4;
     j.epoch = e;
-    long long ctas = (total4 + 256 * 8 - 1) / (256 * 8);
+    long long ctas = (total4 + kPullThreads - 1) / kPullThreads;
     if (ctas < 1) ctas = 1;
-    if (ctas > num_sms()) ctas = num_sms();
-    tile_exchange_kernel<<<(unsigned)ctas, 256, 0, st>>>(j);
+    if (ctas > 2 * num_sms()) ctas = 2 * num_sms();
+    tile_exchange_kernel<<<(unsigned)ctas, kPullThreads, 0, st>>>(j);
     count_launch();
     s->ack_pending = true;
     return check_launch("tile exchange");
