@@ -248,6 +248,24 @@ int scipnp_admm_denoise_host(const float *y, const float *Phi, const float *x0,
  * identical parameters; this frees it.                                          */
 int scipnp_host_release(void);
 
+/* Host-buffer pipeline: a stream of reconstructions with one parameter set -- the frame loop of
+ * admmdenoise_cacti (PnP_SCI/python/pnp_sci_algo.py:498-529: one gap_denoise / admm_denoise per
+ * coded frame) or a camera feed.  `depth` solver handles with a stream each; submit() enqueues
+ * H2D copies -> solve -> D2H copy and returns at once, wait() blocks until x_out of that ticket is
+ * complete (redoing the solve on the exact path if the TV early stop fired).  With page-locked
+ * host buffers the copies of one reconstruction run under the kernels of the next.  At most
+ * `depth` tickets may be in flight; host buffers stay untouched until their ticket was waited
+ * for.  psnr_all (with X_orig): up to psnr_cap values, iters*B of them are written.  refined_iters
+ * sums the iterations redone on the exact path (it resets when a slot is reused).              */
+typedef struct scipnp_pipeline scipnp_pipeline;
+int scipnp_pipeline_create(const scipnp_params *p, int depth, scipnp_pipeline **out);
+int scipnp_pipeline_destroy(scipnp_pipeline *pl);
+int scipnp_pipeline_submit(scipnp_pipeline *pl, const float *y, const float *Phi, const float *x0,
+                           const float *X_orig, int iters, float *x_out, int *ticket);
+int scipnp_pipeline_wait(scipnp_pipeline *pl, int ticket, double *psnr_all, int psnr_cap,
+                         int *psnr_count);
+int scipnp_pipeline_refined_iters(scipnp_pipeline *pl, int *count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -705,4 +705,134 @@ int scipnp_admm_denoise_host(const float* y, const float* Phi, const float* x0, 
     return denoise_host(1, y, Phi, x0, X_orig, p, iters, x_out, psnr_all, psnr_count);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer pipeline: a stream of reconstructions with the same parameters (the frame loop of
+// admmdenoise_cacti, pnp_sci_algo.py:498-529, or a camera feed).  `depth` solver handles, each with
+// its own stream; a submitted reconstruction is  H2D copies -> solve -> D2H copy  on its slot's
+// stream, so the copies of one reconstruction run on the copy engines under the kernels of its
+// neighbours.  Host buffers must be page-locked for the copies to overlap (pageable memory works,
+// serialised by the driver) and must stay valid until the ticket was waited for.
+// ---------------------------------------------------------------------------------------------
+struct scipnp_pipeline {
+    struct Slot {
+        scipnp_solver* s = nullptr;
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+        int* fired_host = nullptr;         // pinned copy of the early-stop flag
+        int ticket = -1;                   // ticket in flight (-1: free)
+        int iters = 0;
+        float* x_out = nullptr;
+    };
+    std::vector<Slot> slots;
+    scipnp_params p{};
+    int next_ticket = 0;
+};
+
+int scipnp_pipeline_destroy(scipnp_pipeline* pl) {
+    if (!pl) return SCIPNP_OK;
+    for (auto& sl : pl->slots) {
+        if (sl.st) cudaStreamSynchronize(sl.st);
+        if (sl.s) scipnp_solver_destroy(sl.s);
+        if (sl.done) cudaEventDestroy(sl.done);
+        if (sl.fired_host) cudaFreeHost(sl.fired_host);
+        if (sl.st) cudaStreamDestroy(sl.st);
+    }
+    delete pl;
+    return SCIPNP_OK;
+}
+
+int scipnp_pipeline_create(const scipnp_params* p, int depth, scipnp_pipeline** out) {
+    SCIPNP_REQUIRE(p && out, "null pointer");
+    SCIPNP_REQUIRE(depth >= 1 && depth <= 8, "pipeline depth must be 1..8");
+    scipnp_pipeline* pl = new (std::nothrow) scipnp_pipeline();
+    if (!pl) { set_error("out of host memory"); return SCIPNP_ENOMEM; }
+    pl->p = *p;
+    pl->slots.resize(depth);
+    for (auto& sl : pl->slots) {
+        int e = scipnp_solver_create(p, &sl.s);
+        if (!e && cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking) != cudaSuccess) e = SCIPNP_ECUDA;
+        if (!e && cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess) e = SCIPNP_ECUDA;
+        if (!e && cudaMallocHost((void**)&sl.fired_host, sizeof(int)) != cudaSuccess) e = SCIPNP_ECUDA;
+        if (e) {
+            if (e == SCIPNP_ECUDA) set_error("pipeline: stream / event / pinned allocation failed");
+            scipnp_pipeline_destroy(pl);
+            return e;
+        }
+    }
+    *out = pl;
+    return SCIPNP_OK;
+}
+
+// wait for the reconstruction in a slot; redo it on the exact path if the early stop fired
+static int pipeline_finish(scipnp_pipeline::Slot& sl) {
+    SCIPNP_CUDA(cudaEventSynchronize(sl.done));
+    scipnp_solver* s = sl.s;
+    if (s->xsnap && *sl.fired_host) {
+        if (int e = scipnp_solver_rollback(s, sl.st)) return e;
+        s->use_fused = false;
+        int e = scipnp_solver_step_async(s, sl.iters, sl.st);
+        s->use_fused = true;
+        if (e) return e;
+        s->refined += sl.iters;
+        const float* src = s->p.method == 0 ? s->xa : s->xproj;
+        SCIPNP_CUDA(cudaMemcpyAsync(sl.x_out, src, s->n_frame * sizeof(float), cudaMemcpyDeviceToHost, sl.st));
+        SCIPNP_CUDA(cudaStreamSynchronize(sl.st));
+    }
+    return SCIPNP_OK;
+}
+
+int scipnp_pipeline_submit(scipnp_pipeline* pl, const float* y, const float* Phi, const float* x0,
+                           const float* X_orig, int iters, float* x_out, int* ticket) {
+    SCIPNP_REQUIRE(pl && y && Phi && x_out && ticket, "null pointer");
+    SCIPNP_REQUIRE(iters >= 0, "negative iteration count");
+    scipnp_pipeline::Slot& sl = pl->slots[pl->next_ticket % pl->slots.size()];
+    if (sl.ticket >= 0) {
+        set_error("pipeline slot still holds ticket %d: wait for it before submitting %d more", sl.ticket,
+                  (int)pl->slots.size());
+        return SCIPNP_ESTATE;
+    }
+    scipnp_solver* s = sl.s;
+    if (int e = scipnp_solver_load(s, y, Phi, nullptr, x0, X_orig, sl.st)) return e;
+    *sl.fired_host = 0;
+    if (s->use_fused) {
+        if (int e = scipnp_solver_begin(s, sl.st)) return e;
+    }
+    if (int e = scipnp_solver_step_async(s, iters, sl.st)) return e;
+    const float* src = s->p.method == 0 ? s->xa : s->xproj;
+    SCIPNP_CUDA(cudaMemcpyAsync(x_out, src, s->n_frame * sizeof(float), cudaMemcpyDeviceToHost, sl.st));
+    if (s->xsnap && s->use_fused)
+        SCIPNP_CUDA(cudaMemcpyAsync(sl.fired_host, s->flags, sizeof(int), cudaMemcpyDeviceToHost, sl.st));
+    SCIPNP_CUDA(cudaEventRecord(sl.done, sl.st));
+    sl.ticket = pl->next_ticket++;
+    sl.iters = iters;
+    sl.x_out = x_out;
+    *ticket = sl.ticket;
+    return SCIPNP_OK;
+}
+
+int scipnp_pipeline_wait(scipnp_pipeline* pl, int ticket, double* psnr_all, int psnr_cap, int* psnr_count) {
+    SCIPNP_REQUIRE(pl, "null pipeline");
+    if (psnr_count) *psnr_count = 0;
+    for (auto& sl : pl->slots) {
+        if (sl.ticket != ticket) continue;
+        int e = pipeline_finish(sl);
+        int cnt = 0;
+        if (!e && psnr_all) e = scipnp_solver_psnr(sl.s, psnr_all, psnr_cap, &cnt, sl.st);
+        if (psnr_count) *psnr_count = cnt;
+        sl.ticket = -1;
+        return e;
+    }
+    set_error("pipeline: unknown or already collected ticket %d", ticket);
+    return SCIPNP_EINVAL;
+}
+
+int scipnp_pipeline_refined_iters(scipnp_pipeline* pl, int* count) {
+    SCIPNP_REQUIRE(pl && count, "null pointer");
+    int n = 0;
+    for (auto& sl : pl->slots) n += sl.s ? sl.s->refined : 0;
+    *count = n;
+    return SCIPNP_OK;
+}
+
 }  // extern "C"

@@ -11,12 +11,12 @@ fallback: importing this package without the built library raises ImportError.
 """
 from . import _lib                                   # fails loudly if the .so is missing
 from ._lib import ScipnpError, LIB_PATH
-from .engine import Solver
+from .engine import Solver, HostPipeline
 from .utils import A_, At_, psnr, phi_sum
 from .pnp_sci_algo import (gap_denoise, admm_denoise, admmdenoise_cacti, gap_denoise_bayer,
                            gap_denoise_cassi, denoise_tv_chambolle)
 
 __version__ = "0.1.0"
-__all__ = ["Solver", "A_", "At_", "psnr", "phi_sum", "gap_denoise", "admm_denoise",
+__all__ = ["Solver", "HostPipeline", "A_", "At_", "psnr", "phi_sum", "gap_denoise", "admm_denoise",
            "admmdenoise_cacti", "gap_denoise_bayer", "gap_denoise_cassi",
            "denoise_tv_chambolle", "ScipnpError", "LIB_PATH"]

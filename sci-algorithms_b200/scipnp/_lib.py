@@ -94,6 +94,11 @@ _SIGS = {
                                           C.POINTER(C.c_double), C.POINTER(_i)]),
     "scipnp_admm_denoise_host": (C.c_int, [_fp, _fp, _fp, _fp, C.POINTER(Params), _i, _fp,
                                            C.POINTER(C.c_double), C.POINTER(_i)]),
+    "scipnp_pipeline_create": (C.c_int, [C.POINTER(Params), _i, C.POINTER(_vp)]),
+    "scipnp_pipeline_destroy": (C.c_int, [_vp]),
+    "scipnp_pipeline_submit": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _i, _fp, C.POINTER(_i)]),
+    "scipnp_pipeline_wait": (C.c_int, [_vp, _i, C.POINTER(C.c_double), _i, C.POINTER(_i)]),
+    "scipnp_pipeline_refined_iters": (C.c_int, [_vp, C.POINTER(_i)]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

@@ -10,7 +10,7 @@ import torch
 
 from ._lib import lib, check, Params, require_device, ScipnpError
 
-__all__ = ["Solver", "to_device", "stream_ptr", "is_torch", "dptr", "f32c"]
+__all__ = ["Solver", "HostPipeline", "make_params", "to_device", "stream_ptr", "is_torch", "dptr", "f32c"]
 
 METHOD_GAP, METHOD_ADMM = 0, 1
 
@@ -48,6 +48,110 @@ def dptr(t):
     if is_torch(t):
         return ct.c_void_p(t.data_ptr())
     return ct.c_void_p(t.ctypes.data)
+
+
+def make_params(B, H, W, C, method="gap", accelerate=True, _lambda=1.0, gamma=0.01, tv_weight=0.1,
+                tv_iter_max=5, tv_eps=2.e-4, phi_batched=False, fused=True, clip=False):
+    """``scipnp_params`` for the given problem (argument names as in pnp_sci_algo.py:536-539)."""
+    p = Params()
+    p.method = METHOD_ADMM if str(method).lower() == "admm" else METHOD_GAP
+    p.accelerate = 1 if accelerate else 0
+    p.lambda_ = float(_lambda)
+    p.gamma = float(gamma)
+    p.tv_weight = float(tv_weight)
+    p.tv_eps = float(tv_eps)
+    p.tv_iter_max = int(tv_iter_max)
+    p.fused = 1 if fused else 0
+    p.B, p.H, p.W, p.C = int(B), int(H), int(W), int(C)
+    p.phi_batched = 1 if phi_batched else 0
+    p.clip01 = 1 if clip else 0
+    return p
+
+
+class HostPipeline:
+    """Stream of reconstructions from host buffers (``scipnp_pipeline_*``): the frame loop of
+    ``admmdenoise_cacti`` (pnp_sci_algo.py:498-529) with the copies of one reconstruction running
+    under the kernels of the next.  ``submit`` returns a ticket at once, ``wait`` returns when the
+    output array of that ticket is complete.  Inputs/outputs are host arrays: NumPy (pageable, the
+    copies then serialise) or pinned CPU tensors (``torch.Tensor.pin_memory``)."""
+
+    def __init__(self, B, H, W, C, depth=2, **kw):
+        require_device()
+        self.shape = (int(B), int(H), int(W), int(C))
+        self.params = make_params(B, H, W, C, **kw)
+        self.depth = int(depth)
+        h = ct.c_void_p()
+        check(lib.scipnp_pipeline_create(ct.byref(self.params), self.depth, ct.byref(h)))
+        self._h = h
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.scipnp_pipeline_destroy(self._h)
+            self._h = None
+            self._keep = {}
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @staticmethod
+    def _host(a, shape, name):
+        if a is None:
+            return None
+        if is_torch(a):
+            if a.is_cuda or a.dtype != torch.float32 or not a.is_contiguous():
+                raise ValueError("%s must be a contiguous float32 host tensor" % name)
+        else:
+            a = f32c(a)
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError("%s has shape %s, expected %s" % (name, tuple(a.shape), tuple(shape)))
+        return a
+
+    def submit(self, y, Phi, iters, out, x0=None, X_orig=None):
+        """Enqueue one reconstruction; ``out`` ([B,H,W,C] host array) is filled when ``wait``
+        returns for the ticket this call hands back."""
+        B, H, W, Cc = self.shape
+        pb = self.params.phi_batched
+        y = self._host(y, (B, H, W), "y")
+        Phi = self._host(Phi, (B, H, W, Cc) if pb else (H, W, Cc), "Phi")
+        x0 = self._host(x0, self.shape, "x0")
+        X_orig = self._host(X_orig, self.shape, "X_orig")
+        if is_torch(out):
+            if out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != self.shape:
+                raise ValueError("out must be a contiguous float32 host tensor of shape %s" % (self.shape,))
+        elif out.dtype != np.float32 or not out.flags.c_contiguous or tuple(out.shape) != self.shape:
+            raise ValueError("out must be a C-contiguous float32 array of shape %s" % (self.shape,))
+        t = ct.c_int(-1)
+        check(lib.scipnp_pipeline_submit(self._h, dptr(y), dptr(Phi), dptr(x0), dptr(X_orig), int(iters),
+                                         dptr(out), ct.byref(t)))
+        self._keep[t.value] = (y, Phi, x0, X_orig, out, int(iters), X_orig is not None)
+        return t.value
+
+    def wait(self, ticket):
+        """Block until the ticket's output is complete; returns (out, psnr_all or None)."""
+        n = ct.c_int(0)
+        if ticket not in self._keep:             # unknown / collected: let the library say so
+            check(lib.scipnp_pipeline_wait(self._h, int(ticket), None, 0, ct.byref(n)))
+        y, Phi, x0, X_orig, out, iters, has_orig = self._keep.pop(ticket)
+        if has_orig:
+            cap = iters * self.shape[0]
+            buf = (ct.c_double * max(cap, 1))()
+            check(lib.scipnp_pipeline_wait(self._h, int(ticket), buf, cap, ct.byref(n)))
+            psnr = np.array(buf[:n.value], dtype=np.float64).reshape(-1, self.shape[0])
+            return out, psnr
+        check(lib.scipnp_pipeline_wait(self._h, int(ticket), None, 0, ct.byref(n)))
+        return out, None
+
+    @property
+    def refined_iters(self):
+        n = ct.c_int(0)
+        check(lib.scipnp_pipeline_refined_iters(self._h, ct.byref(n)))
+        return n.value
 
 
 class Solver:

@@ -333,6 +333,45 @@ def test_c_abi_host_entry_matches_python_surface(sp, golden):
     assert lib.scipnp_launch_count() > 0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [True, False])
+def test_host_pipeline_matches_one_call_entries(sp, golden, fused):
+    """scipnp_pipeline_*: three different measurements through two slots give what the
+    synchronous solver gives, in submission order, PSNR track included; a full pipeline refuses
+    a further submit."""
+    import torch
+    from scipnp import HostPipeline, Solver, ScipnpError
+    g = golden("gap_acc")
+    H, W, Cc = g["mask"].shape
+    Phi = np.ascontiguousarray(g["mask"], np.float32)
+    Xo = np.ascontiguousarray(g["X_orig"], np.float32)
+    ys = [np.ascontiguousarray(g["y"] * np.float32(s), np.float32) for s in (1.0, 0.5, 0.25)]
+    kw = dict(method="gap", tv_weight=0.3, tv_iter_max=5, fused=fused)
+    want = []
+    with Solver(1, H, W, Cc, **kw) as so:
+        for y in ys:
+            so.load(y[None], Phi, X_orig=Xo[None])
+            so.run(12)
+            want.append((so.get_x()[0].copy(), np.array(so.psnr_all())))
+    outs = [torch.empty((1, H, W, Cc), dtype=torch.float32).pin_memory() for _ in ys]
+    with HostPipeline(1, H, W, Cc, depth=2, **kw) as pl:
+        t0 = pl.submit(torch.from_numpy(ys[0][None]).pin_memory(), Phi, 12, outs[0], X_orig=Xo[None])
+        t1 = pl.submit(ys[1][None], Phi, 12, outs[1], X_orig=Xo[None])
+        with pytest.raises(ScipnpError):
+            pl.submit(ys[2][None], Phi, 12, outs[2])
+        x0, p0 = pl.wait(t0)
+        t2 = pl.submit(ys[2][None], Phi, 12, outs[2], X_orig=Xo[None])
+        res = [(x0, p0), pl.wait(t1), pl.wait(t2)]
+        with pytest.raises(ScipnpError):
+            pl.wait(t2)                        # already collected
+    for (x, ps), (xw, pw) in zip(res, want):
+        np.testing.assert_array_equal(x.numpy()[0], xw)
+        # squared errors are summed with atomics: equal up to the summation order
+        np.testing.assert_allclose(ps.reshape(-1), pw.reshape(-1), rtol=0, atol=1e-9)
+    if not fused:                              # the exact path is the reference bit for bit
+        assert np.abs(res[0][0].numpy()[0] - g["x"]).max() <= TOL_EXACT
+
+
 def test_c_abi_rejects_bad_arguments(sp):
     from scipnp._lib import lib
     assert lib.scipnp_A(None, None, None, 1, 4, 4, 4, 0, None) == -1
