@@ -21,6 +21,7 @@ constexpr int BOX_BYTES = RB * 32 * 16;   // RB rows x 32 pixels x one 4-channel
 // worse for K = 4, 8 -- those keep one box per chunk (SUBK = 1, chunk-major, conflict-free).
 __host__ __device__ constexpr int fused_subk(int K) { return (K & 3) == 0 ? 1 : K; }
 constexpr int kMaxWarps = 8;
+constexpr int kSegCost = 12;      // cost of starting a row segment, in rows (see the work split in the kernel)
 
 struct FusedParams {
     const float* x_in; float* x_out;
@@ -273,7 +274,11 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     //      consecutive units, i.e. at most a few row segments of neighbouring strips.  No wave
     //      quantisation, and the warm-up rows of a segment are paid once or twice per CTA.
     const int nbundles = (p.ngroups + NG - 1) / NG;
-    const long long total = (long long)p.B * nbundles * H;
+    // Every strip is charged kSegCost extra units in front of its H rows: a CTA whose share crosses a
+    // strip boundary starts a second segment there (warm-up and drain rows, a pipeline refill, masked
+    // first and last blocks), so it is given that many rows less.
+    const int Hv = H + kSegCost;
+    const long long total = (long long)p.B * nbundles * Hv;
     const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
     long long unit = (long long)blockIdx.x * per_cta;
     const long long unit_end = min(total, unit + per_cta);
@@ -284,10 +289,12 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     const bool split = SPLIT && p.small_tma;
 #pragma unroll 1
     while (unit < unit_end) {
-    const int strip = (int)(unit / H);
-    const int r0 = (int)(unit - (long long)strip * H);
-    const int r1 = (int)min((long long)H, r0 + (unit_end - unit));
-    unit += r1 - r0;
+    const int strip = (int)(unit / Hv);
+    const int v0 = (int)(unit - (long long)strip * Hv);                    // position in the charged strip
+    const int v1 = (int)min((long long)Hv, v0 + (unit_end - unit));
+    unit += v1 - v0;
+    const int r0 = max(v0 - kSegCost, 0), r1 = v1 - kSegCost;
+    if (r1 <= r0) continue;                                                // only charge units: no rows here
     const int b = strip / nbundles;
     const int group0 = (strip - b * nbundles) * NG;      // first pixel group of this segment
     const int grp = group0 + gi;
@@ -609,7 +616,7 @@ int launch_stream_k(FusedParams fp, const FusedMaps& maps, dim3 grid, cudaStream
     // (see the kernel).  Large scenes fill all slots; small ones get segments of at least 8 rows.
     const long long slots = (long long)ctas_per_sm * num_sms();
     const long long nbundles = (fp.ngroups + fused_groups(K) - 1) / fused_groups(K);
-    const long long total = (long long)fp.B * nbundles * fp.H;
+    const long long total = (long long)fp.B * nbundles * (fp.H + kSegCost);
     long long n = total / 8;      // small scenes are latency-bound: short segments, more CTAs
     if (n > slots) n = slots;
     if (n < 1) n = 1;
