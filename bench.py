@@ -206,7 +206,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # -- our arm -----------------------------------------------------------------------------------
@@ -386,12 +386,33 @@ def run_ours(args):
             line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    from C when NCCL_DEBUG is set in the environment), so file descriptor 1 points at stderr for the
+    whole run and is restored for the final line only."""
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
