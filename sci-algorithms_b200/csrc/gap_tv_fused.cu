@@ -10,11 +10,14 @@
 //   * a warp owns 32 consecutive pixels (lane = pixel) of one 4-channel chunk and
 //     walks down the rows of its segment; the K = C/4 chunk-warps of a pixel group
 //     sit in the same CTA because the projection couples the channels of a pixel;
-//   * rows are staged global -> shared by the TMA unit (4-D tensor maps over
-//     [rows][W][C/4][4]: a box is RB rows x 32 pixels x one chunk, so the tiles arrive
-//     transposed to chunk-major and the lane-per-pixel LDS.128 is conflict-free; pixels
-//     outside the image are zero-filled), three-slot ring, one mbarrier per slot;
-//   * step rho: stage 0 turns row rho into f = x + lambda*s*Phi; stage i (1..R,
+//   * rows are staged global -> shared by the TMA unit in blocks of 4 rows (3-D tensor
+//     maps over [rows][W][C]: a box is 4 rows x 32 pixels x whole pixels, i.e. contiguous
+//     rows of global memory; pixels outside the image are zero-filled), four-slot ring,
+//     one mbarrier per slot;
+//   * phase A, once per staged block: one thread per (row, pixel) forms the dot product
+//     over all C channels, updates y1 and leaves lambda*s in a shared-memory plane; a
+//     split arrive/wait on a fifth mbarrier publishes it, so warps may drift by a block;
+//   * step rho: stage 0 turns row rho into f = x + (lambda*s)*Phi; stage i (1..R,
 //     R = tv_iter_max-1) advances dual iteration i on row rho-i using the row it
 //     kept from the previous step, so out_R(rho-R) leaves the pipeline every step.
 //     Horizontal neighbours come from warp shuffles (out from lane+1, p1 from
