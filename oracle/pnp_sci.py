@@ -165,6 +165,51 @@ def joint_admm_denoise(y, Phi_sum, A, At, _lambda=1, gamma=0.0, accelerate=None,
     return x, ps, ss, psnr_all
 
 
+def gap_multistep_denoise(y, Phi_sum, A, At, second, _lambda=1, accelerate=True,
+                          denoiser='tv+ffdnet', iter_max=50, noise_estimate=False, sigma=None,
+                          tv_weight=0.1, tv_iter_max=5, multichannel=True, x0=None, X_orig=None,
+                          model=None, show_iqa=True, tvm='tv_chambolle'):
+    """TV + second-denoiser period of the joint module (joint_pnp_sci_algo.py:309-500): every
+    iteration is the GAP projection (:412-417), the Chambolle TV step (:428-429; 'ITV3D_FGP' and
+    'ITV2D_cham' name functions that do not exist in that file, so only 'tv_chambolle' runs) and
+    then a learned denoiser ``x = second(x, nsig, model)`` (:441, :466 -- FFDNet / FastDVDnet in
+    the reference, absent here and injected by the caller).  PSNR is taken after both (:473)."""
+    if denoiser.lower() not in ('tv+ffdnet', 'tv+fastdvdnet'):
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    if tvm != 'tv_chambolle':
+        raise ValueError('Unsupported TV denoiser {}!'.format(tvm))
+    if x0 is None:
+        x0 = At(y)
+    sigma, iter_max = _as_schedule(sigma, iter_max)
+    y1 = np.zeros_like(y)
+    x = x0
+    psnr_all = []
+    for idx, nsig in enumerate(sigma):
+        for _it in range(iter_max[idx]):
+            yb = A(x)
+            if accelerate:
+                y1 = y1 + (y - yb)
+                x = x + _lambda * (At((y1 - yb) / Phi_sum))
+            else:
+                x = x + _lambda * (At((y - yb) / Phi_sum))
+            x = denoise_tv_chambolle(x, tv_weight, n_iter_max=tv_iter_max, multichannel=multichannel)
+            x = second(x, nsig, model)
+            if show_iqa and X_orig is not None:
+                psnr_all.append(psnr(X_orig, x))
+    ps, ss = _frame_iqa(X_orig, x)
+    return x, ps, ss, psnr_all
+
+
+def gap_joint_denoise(y, Phi_sum, A, At, second, x0=None, X_orig=None, denoiser='tv+ffdnet',
+                      iter_max1=50, iter_max2=50, sigma1=None, sigma2=None, **args):
+    """Two periods (joint_pnp_sci_algo.py:100-116): GAP-TV, then the TV + second-denoiser loop
+    started from its result; returns what the second period returns."""
+    x, _, _, _ = gap_denoise(y, Phi_sum, A, At, x0=x0, X_orig=X_orig, denoiser='tv',
+                             iter_max=iter_max1, sigma=sigma1, **args)
+    return gap_multistep_denoise(y, Phi_sum, A, At, second, x0=x, X_orig=X_orig, denoiser=denoiser,
+                                 iter_max=iter_max2, sigma=sigma2, **args)
+
+
 # -- R7 -----------------------------------------------------------------------
 
 def admmdenoise_cacti(meas, mask, A, At, projmeth='admm', v0=None, orig=None,

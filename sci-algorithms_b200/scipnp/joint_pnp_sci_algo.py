@@ -4,20 +4,25 @@
     admm_denoise   joint_pnp_sci_algo.py:502-665   ADMM-TV with ``theta = clip(theta, 0, 1)`` (:633)
     gap_denoise    joint_pnp_sci_algo.py:666-...    same loop as pnp_sci_algo.gap_denoise
 
-The two-period drivers (``gap_joint_denoise`` / ``admm_joint_denoise``, :81-116) run a TV period
-and then a TV+CNN period; their first period is exactly the functions below, the CNN period is
-outside the hot path.  ``tvm`` may be 'tv_chambolle', 'ITV3D_FGP' or 'ITV2D_cham' in ``admm_denoise``:
+    gap_multistep_denoise  :309-500   TV + learned-denoiser period: projection and TV on the
+                                      device, hand-off of the device tensor to the caller's denoiser
+    gap_joint_denoise      :100-116   GAP-TV period, then the period above from its result
+
+The learned denoisers themselves (``packages/ffdnet``, ``packages/fastdvdnet``) are outside this
+engine: the TV+CNN period takes the second denoiser as a callable that receives the CUDA tensor.  ``tvm`` may be 'tv_chambolle', 'ITV3D_FGP' or 'ITV2D_cham' in ``admm_denoise``:
 the reference calls ``denoise_tv_chambolle`` for all three (:606-611).
 """
 import numpy as np
+import torch
 
 from . import pnp_sci_algo as _base
 from .pnp_sci_algo import _check_tv, _recover_phi, _host, _total_iters, _progress
 from .engine import Solver, f32c
 from .iqa import frames_iqa
+from .tiled import _wrap
 from .utils import A_, At_, psnr  # noqa: F401
 
-__all__ = ["admm_denoise", "gap_denoise", "A_", "At_", "psnr"]
+__all__ = ["admm_denoise", "gap_denoise", "gap_multistep_denoise", "gap_joint_denoise", "A_", "At_", "psnr"]
 
 
 def admm_denoise(y, Phi_sum, A=None, At=None, _lambda=1, gamma=0.0, accelerate=None,
@@ -56,3 +61,66 @@ def gap_denoise(y, Phi_sum, A=None, At=None, _lambda=1, gamma=None, accelerate=T
                              sigma=sigma, tv_weight=tv_weight, tv_iter_max=tv_iter_max,
                              multichannel=multichannel, x0=x0, X_orig=X_orig, model=model,
                              show_iqa=show_iqa, tvm=tvm, Phi=Phi)
+
+
+def gap_multistep_denoise(y, Phi_sum, A=None, At=None, _lambda=1, accelerate=True,
+                          denoiser='tv+ffdnet', iter_max=50, noise_estimate=False, sigma=None,
+                          tv_weight=0.1, tv_iter_max=5, multichannel=True, x0=None, X_orig=None,
+                          model=None, show_iqa=True, tvm='tv_chambolle', Phi=None,
+                          second_denoiser=None):
+    """TV + learned-denoiser period (joint_pnp_sci_algo.py:309-500).  Every iteration runs the GAP
+    projection and the Chambolle TV step as one fused launch, then hands the current estimate --
+    a float32 CUDA tensor ``[H, W, C]`` aliasing the solver's buffer -- to
+    ``second_denoiser(x_dev, nsig, model)``, which changes it in place or returns a tensor of the
+    same shape (the slot of ``ffdnet_vdenoiser`` :441 / ``fastdvdnet_denoiser`` :466).  Nothing
+    leaves the device between the two steps.  PSNR is taken after both (:473), like the reference.
+    """
+    if str(denoiser).lower() not in ('tv+ffdnet', 'tv+fastdvdnet'):
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    if tvm != 'tv_chambolle':                  # the other names call functions the reference never defines
+        raise ValueError('Unsupported TV denoiser {}!'.format(tvm))
+    if not multichannel:
+        raise NotImplementedError("multichannel=False is not on the reference's hot path")
+    if second_denoiser is None:
+        raise NotImplementedError(
+            "the learned denoisers of the reference (packages/ffdnet, packages/fastdvdnet) are not part "
+            "of this engine: pass second_denoiser=callable(x_dev, nsig, model)")
+    Phi = _recover_phi(A, At, y, Phi)
+    yh = f32c(_host(y))
+    Xo = None if X_orig is None else f32c(_host(X_orig))
+    H, W, Cc = Phi.shape
+    if not isinstance(sigma, list):
+        sigma = [sigma]
+    if not isinstance(iter_max, list):
+        iter_max = [iter_max] * len(sigma)
+    psnr_all = []
+    with Solver(1, H, W, Cc, method="gap", accelerate=accelerate, _lambda=_lambda, tv_weight=tv_weight,
+                tv_iter_max=tv_iter_max, fused=_base.USE_FUSED) as s:
+        s.load(yh[None], Phi, Phi_sum=f32c(_host(Phi_sum)),
+               x0=None if x0 is None else f32c(_host(x0))[None])
+        dev = torch.device("cuda", torch.cuda.current_device())
+        Xd = None if (Xo is None or not show_iqa) else torch.from_numpy(Xo).to(dev)
+        for idx, nsig in enumerate(sigma):
+            for _ in range(int(iter_max[idx])):
+                s.run(1)                                           # projection + TV (:412-429)
+                xv = _wrap(s.state_ptrs()[0], (H, W, Cc), dev)     # the estimate, in place
+                out = second_denoiser(xv, nsig, model)             # :441 / :466
+                if out is not None and out is not xv:
+                    xv.copy_(out.to(dev, torch.float32).reshape(H, W, Cc))
+                if Xd is not None:
+                    psnr_all.append(psnr(Xd, xv))                  # :473
+        x = s.get_x()[0]
+    ps, ss = frames_iqa(Xo, x)
+    return x, ps, ss, psnr_all
+
+
+def gap_joint_denoise(y, Phi_sum, A=None, At=None, x0=None, X_orig=None, denoiser='tv+ffdnet',
+                      iter_max1=50, iter_max2=50, sigma1=None, sigma2=None, **args):
+    """Two periods (joint_pnp_sci_algo.py:100-116): GAP-TV, then ``gap_multistep_denoise`` from its
+    result; returns what the second period returns.  ``second_denoiser=`` (and ``Phi=``) travel in
+    ``args`` like the reference's other keyword arguments."""
+    second = args.pop("second_denoiser", None)
+    x, _, _, _ = gap_denoise(y, Phi_sum, A, At, x0=x0, X_orig=X_orig, denoiser='tv',
+                             iter_max=iter_max1, sigma=sigma1, **args)
+    return gap_multistep_denoise(y, Phi_sum, A, At, x0=x, X_orig=X_orig, denoiser=denoiser,
+                                 iter_max=iter_max2, sigma=sigma2, second_denoiser=second, **args)

@@ -26,6 +26,13 @@ from oracle import reference_loader, tv_chambolle, pnp_sci as opnp  # noqa: E402
 from scipnp import synth  # noqa: E402
 
 
+def second_standin(x, nsig, model=None):
+    """Stand-in for the learned denoiser of the TV+CNN period (same arithmetic in
+    tests/test_gpu_parity.py with torch): an affine shrink that depends on the noise level."""
+    a = np.float32(1.0 - 0.1 * float(nsig))
+    return np.clip(x * a + np.float32(0.01), 0, 1).astype(np.float32)
+
+
 def save(name, **arrs):
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **arrs)
@@ -90,6 +97,25 @@ def main():
                                            iter_max=12, tv_weight=0.3, tv_iter_max=5, X_orig=Xo)
     save("joint_admm", y=y, mask=mask, X_orig=Xo, x=x, psnr=np.array(ps), ssim=np.array(ss),
          psnr_all=np.array(pa), iter_max=12, tv_weight=0.3, tv_iter_max=5, _lambda=1.0, gamma=0.0)
+
+    # TV + learned-denoiser period and the two-period driver of the joint module.
+    # The reference's FFDNet is absent; a fixed elementwise stand-in is injected in its place so
+    # that the reference's own loop (projection, TV, hand-off, PSNR) produces the vectors.
+    ref_joint.ffdnet_vdenoiser = second_standin
+    x, ps, ss, pa = ref_joint.gap_multistep_denoise(y, ms, A, At, _lambda=1, accelerate=True,
+                                                    denoiser='tv+ffdnet', iter_max=[3, 3],
+                                                    sigma=[0.2, 0.1], tv_weight=0.3, tv_iter_max=5,
+                                                    X_orig=Xo)
+    save("joint_multistep", y=y, mask=mask, X_orig=Xo, x=x, psnr=np.array(ps), ssim=np.array(ss),
+         psnr_all=np.array(pa), iter_max=np.array([3, 3]), sigma=np.array([0.2, 0.1]), tv_weight=0.3,
+         tv_iter_max=5)
+    x, ps, ss, pa = ref_joint.gap_joint_denoise(y, ms, A, At, X_orig=Xo, denoiser='tv+ffdnet',
+                                                iter_max1=4, iter_max2=[2, 2], sigma1=None,
+                                                sigma2=[0.2, 0.1], _lambda=1, accelerate=True,
+                                                tv_weight=0.3, tv_iter_max=5)
+    save("joint_two_period", y=y, mask=mask, X_orig=Xo, x=x, psnr=np.array(ps), ssim=np.array(ss),
+         psnr_all=np.array(pa), iter_max1=4, iter_max2=np.array([2, 2]), sigma2=np.array([0.2, 0.1]),
+         tv_weight=0.3, tv_iter_max=5)
 
     # warm start + ragged channel count (C=5, odd sizes)
     meas5, mask5, orig5 = cacti(33, 29, 5, 1, cfg=12)

@@ -532,6 +532,43 @@ def test_joint_admm_clip_golden(sp, golden, path):
         J.admm_denoise(g["y"], _psum(g["mask"]), A, At, denoiser='ffdnet', iter_max=1)
 
 
+def test_joint_multistep_and_two_period_golden(sp, golden, path):
+    """the TV + learned-denoiser period (projection and TV fused on the device, the
+    estimate handed to the second denoiser as a CUDA tensor) and the two-period driver, against
+    the reference's own loops run with the same stand-in in FFDNet's place."""
+    import torch
+    from scipnp import joint_pnp_sci_algo as J
+    seen = []
+
+    def second(x_dev, nsig, model=None):          # make_golden.py: second_standin, in torch
+        assert x_dev.is_cuda and x_dev.dtype == torch.float32
+        seen.append(float(nsig))
+        a = float(np.float32(1.0 - 0.1 * float(nsig)))
+        x_dev.mul_(a).add_(float(np.float32(0.01))).clamp_(0, 1)
+
+    g = golden("joint_multistep")
+    A, At = _ops(g["mask"])
+    ms = _psum(g["mask"])
+    x, ps, ss, pa = J.gap_multistep_denoise(g["y"], ms, A, At, denoiser='tv+ffdnet', iter_max=[3, 3],
+                                            sigma=[0.2, 0.1], tv_weight=0.3, tv_iter_max=5,
+                                            X_orig=g["X_orig"], second_denoiser=second)
+    assert seen == [0.2] * 3 + [0.1] * 3
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+    assert np.abs(np.array(ps) - g["psnr"]).max() <= TOL_DB
+    g = golden("joint_two_period")
+    x, ps, ss, pa = J.gap_joint_denoise(g["y"], ms, A, At, X_orig=g["X_orig"], denoiser='tv+ffdnet',
+                                        iter_max1=4, iter_max2=[2, 2], sigma1=None, sigma2=[0.2, 0.1],
+                                        _lambda=1, accelerate=True, tv_weight=0.3, tv_iter_max=5,
+                                        second_denoiser=lambda xd, ns, m: torch.clamp(
+                                            xd * float(np.float32(1.0 - 0.1 * ns)) + float(np.float32(0.01)), 0, 1))
+    assert len(pa) == 4
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+    with pytest.raises(NotImplementedError):       # the CNNs themselves are not part of the engine
+        J.gap_multistep_denoise(g["y"], ms, A, At, iter_max=1, sigma=0.1)
+    with pytest.raises(ValueError):
+        J.gap_multistep_denoise(g["y"], ms, A, At, denoiser='tv', iter_max=1, second_denoiser=second)
+
+
 def test_c_abi_kernel_entries_directly(sp):
     """The stateless C entries called with raw device pointers: one fused iteration equals
     scipnp_gap_project + scipnp_tv_chambolle, and the ADMM pieces compose to the reference update."""

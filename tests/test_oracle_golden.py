@@ -147,3 +147,32 @@ def test_joint_admm_clip(golden):
     np.testing.assert_array_equal(x, g["x"])
     np.testing.assert_array_equal(np.array(pa), g["psnr_all"])
     np.testing.assert_array_equal(np.array(ps), g["psnr"])
+
+
+def _second_standin(x, nsig, model=None):
+    # the stand-in of tests/golden/make_golden.py for the learned denoiser
+    a = np.float32(1.0 - 0.1 * float(nsig))
+    return np.clip(x * a + np.float32(0.01), 0, 1).astype(np.float32)
+
+
+def test_joint_multistep_and_two_period(golden):
+    """TV + second-denoiser period and the two-period driver of the joint module, against the
+    reference's own loops run with the same stand-in in FFDNet's place."""
+    g = golden("joint_multistep")
+    A, At = _ops(g["mask"])
+    ms = O.phi_sum(g["mask"])
+    x, ps, ss, pa = O.gap_multistep_denoise(g["y"], ms, A, At, _second_standin, iter_max=[3, 3],
+                                            sigma=[0.2, 0.1], tv_weight=0.3, tv_iter_max=5,
+                                            X_orig=g["X_orig"])
+    np.testing.assert_array_equal(x, g["x"])
+    np.testing.assert_array_equal(np.array(pa), g["psnr_all"])
+    np.testing.assert_array_equal(np.array(ps), g["psnr"])
+    g = golden("joint_two_period")
+    x, ps, ss, pa = O.gap_joint_denoise(g["y"], ms, A, At, _second_standin, X_orig=g["X_orig"],
+                                        iter_max1=4, iter_max2=[2, 2], sigma1=None, sigma2=[0.2, 0.1],
+                                        _lambda=1, accelerate=True, tv_weight=0.3, tv_iter_max=5)
+    assert len(pa) == 4                      # the PSNR track of the second period only
+    np.testing.assert_array_equal(x, g["x"])
+    np.testing.assert_array_equal(np.array(pa), g["psnr_all"])
+    with pytest.raises(ValueError):
+        O.gap_multistep_denoise(g["y"], ms, A, At, _second_standin, denoiser='tv', iter_max=1)
