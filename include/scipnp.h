@@ -206,6 +206,11 @@ int scipnp_solver_sqerr(scipnp_solver *s, double *sums_host, int cap, int *count
 int scipnp_solver_refined_iters(scipnp_solver *s, int *count);
 /* Device pointers of the state, for callers that manage halos themselves.      */
 int scipnp_solver_state(scipnp_solver *s, float **x_cur, float **y1_cur);
+/* ADMM handles: device pointers of theta (the TV output), of the multiplier b and of x, the
+ * projection output that admm_denoise returns (pnp_sci_algo.py:809).  For callers that put a
+ * second denoiser between the TV step and the multiplier update
+ * (joint_pnp_sci_algo.py:118-306, admm_multistep_denoise).                       */
+int scipnp_solver_admm_state(scipnp_solver *s, float **theta, float **b, float **x);
 /* Kernel launches issued since this handle was created.                        */
 long long scipnp_solver_launch_count(scipnp_solver *s);
 /* 1 when the handle runs the one-pass fused iteration, 0 on the exact path.    */

@@ -210,6 +210,49 @@ def gap_joint_denoise(y, Phi_sum, A, At, second, x0=None, X_orig=None, denoiser=
                                  iter_max=iter_max2, sigma=sigma2, **args)
 
 
+def admm_multistep_denoise(y, Phi_sum, A, At, second, _lambda=1, gamma=0.0, accelerate=None,
+                           denoiser='tv+ffdnet', iter_max=50, noise_estimate=False, sigma=None,
+                           tv_weight=0.1, tv_iter_max=5, multichannel=True, x0=None, model=None,
+                           X_orig=None, show_iqa=True, tvm='tv_chambolle'):
+    """ADMM twin of ``gap_multistep_denoise`` (joint_pnp_sci_algo.py:118-306): projection (:213-214),
+    ``theta = TV(x - b)`` (:230; 'ITV3D_FGP' and 'ITV2D_cham' call the same function here),
+    ``theta = second(theta, nsig, model)`` (:242, :263), clip to [0, 1] (:268), multiplier (:270);
+    PSNR of ``x`` (:273) and ``x`` is returned."""
+    if denoiser.lower() not in ('tv+ffdnet', 'tv+fastdvdnet'):
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    if tvm not in ('tv_chambolle', 'ITV3D_FGP', 'ITV2D_cham'):
+        raise ValueError('Unsupported TV denoiser {}!'.format(tvm))
+    if x0 is None:
+        x0 = At(y)
+    sigma, iter_max = _as_schedule(sigma, iter_max)
+    x = x0
+    theta = x0
+    b = np.zeros_like(x0)
+    psnr_all = []
+    for idx, nsig in enumerate(sigma):
+        for _it in range(iter_max[idx]):
+            yb = A(theta + b)
+            x = (theta + b) + _lambda * (At((y - yb) / (Phi_sum + gamma)))
+            theta = denoise_tv_chambolle(x - b, tv_weight, n_iter_max=tv_iter_max, multichannel=multichannel)
+            theta = second(theta, nsig, model)
+            theta = np.clip(theta, 0, 1)
+            b = b - (x - theta)
+            if show_iqa and X_orig is not None:
+                psnr_all.append(psnr(X_orig, x))
+    ps, ss = _frame_iqa(X_orig, x)
+    return x, ps, ss, psnr_all
+
+
+def admm_joint_denoise(y, Phi_sum, A, At, second, x0=None, X_orig=None, denoiser='tv+ffdnet',
+                       iter_max1=50, iter_max2=50, sigma1=None, sigma2=None, **args):
+    """Two periods (joint_pnp_sci_algo.py:81-98): the joint module's ADMM-TV, then
+    ``admm_multistep_denoise`` started from its result."""
+    x, _, _, _ = joint_admm_denoise(y, Phi_sum, A, At, x0=x0, X_orig=X_orig, denoiser='tv',
+                                    iter_max=iter_max1, sigma=sigma1, **args)
+    return admm_multistep_denoise(y, Phi_sum, A, At, second, x0=x, X_orig=X_orig, denoiser=denoiser,
+                                  iter_max=iter_max2, sigma=sigma2, **args)
+
+
 # -- R7 -----------------------------------------------------------------------
 
 def admmdenoise_cacti(meas, mask, A, At, projmeth='admm', v0=None, orig=None,

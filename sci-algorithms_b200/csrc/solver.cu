@@ -416,6 +416,15 @@ int scipnp_solver_state(scipnp_solver* s, float** x_cur, float** y1_cur) {
     return SCIPNP_OK;
 }
 
+int scipnp_solver_admm_state(scipnp_solver* s, float** theta, float** b, float** x) {
+    SCIPNP_REQUIRE(s, "null solver");
+    if (s->p.method != 1) { set_error("not an ADMM handle"); return SCIPNP_ESTATE; }
+    if (theta) *theta = s->xa;
+    if (b) *b = s->ba;
+    if (x) *x = s->xproj;
+    return SCIPNP_OK;
+}
+
 int scipnp_solver_uses_fused(scipnp_solver* s) { return s && s->use_fused ? 1 : 0; }
 
 long long scipnp_solver_launch_count(scipnp_solver* s) { return s ? g_launches - s->launches0 : 0; }

@@ -87,6 +87,7 @@ _SIGS = {
     "scipnp_solver_sqerr": (C.c_int, [_vp, C.POINTER(C.c_double), _i, C.POINTER(_i), _vp]),
     "scipnp_solver_refined_iters": (C.c_int, [_vp, C.POINTER(_i)]),
     "scipnp_solver_state": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "scipnp_solver_admm_state": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "scipnp_solver_launch_count": (C.c_longlong, [_vp]),
     "scipnp_solver_uses_fused": (C.c_int, [_vp]),
     "scipnp_host_release": (C.c_int, []),

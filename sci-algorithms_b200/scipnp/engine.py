@@ -309,6 +309,12 @@ class Solver:
     def launches(self):
         return int(lib.scipnp_solver_launch_count(self._h))
 
+    def admm_state_ptrs(self):
+        """(theta, b, x) device pointers of an ADMM handle."""
+        t, b, x = ct.c_void_p(), ct.c_void_p(), ct.c_void_p()
+        check(lib.scipnp_solver_admm_state(self._h, ct.byref(t), ct.byref(b), ct.byref(x)))
+        return t.value, b.value, x.value
+
     def state_ptrs(self):
         a, b = ct.c_void_p(), ct.c_void_p()
         check(lib.scipnp_solver_state(self._h, ct.byref(a), ct.byref(b)))

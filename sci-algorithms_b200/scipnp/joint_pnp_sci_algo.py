@@ -7,6 +7,8 @@
     gap_multistep_denoise  :309-500   TV + learned-denoiser period: projection and TV on the
                                       device, hand-off of the device tensor to the caller's denoiser
     gap_joint_denoise      :100-116   GAP-TV period, then the period above from its result
+    admm_multistep_denoise :118-306   the ADMM twin (second denoiser between TV and the multiplier)
+    admm_joint_denoise     :81-98     ADMM-TV period, then the period above from its result
 
 The learned denoisers themselves (``packages/ffdnet``, ``packages/fastdvdnet``) are outside this
 engine: the TV+CNN period takes the second denoiser as a callable that receives the CUDA tensor.  ``tvm`` may be 'tv_chambolle', 'ITV3D_FGP' or 'ITV2D_cham' in ``admm_denoise``:
@@ -22,7 +24,8 @@ from .iqa import frames_iqa
 from .tiled import _wrap
 from .utils import A_, At_, psnr  # noqa: F401
 
-__all__ = ["admm_denoise", "gap_denoise", "gap_multistep_denoise", "gap_joint_denoise", "A_", "At_", "psnr"]
+__all__ = ["admm_denoise", "gap_denoise", "gap_multistep_denoise", "gap_joint_denoise",
+           "admm_multistep_denoise", "admm_joint_denoise", "A_", "At_", "psnr"]
 
 
 def admm_denoise(y, Phi_sum, A=None, At=None, _lambda=1, gamma=0.0, accelerate=None,
@@ -124,3 +127,69 @@ def gap_joint_denoise(y, Phi_sum, A=None, At=None, x0=None, X_orig=None, denoise
                              iter_max=iter_max1, sigma=sigma1, **args)
     return gap_multistep_denoise(y, Phi_sum, A, At, x0=x, X_orig=X_orig, denoiser=denoiser,
                                  iter_max=iter_max2, sigma=sigma2, second_denoiser=second, **args)
+
+
+def admm_multistep_denoise(y, Phi_sum, A=None, At=None, _lambda=1, gamma=0.0, accelerate=None,
+                           denoiser='tv+ffdnet', iter_max=50, noise_estimate=False, sigma=None,
+                           tv_weight=0.1, tv_iter_max=5, multichannel=True, x0=None, model=None,
+                           X_orig=None, show_iqa=True, tvm='tv_chambolle', Phi=None,
+                           second_denoiser=None):
+    """ADMM twin of ``gap_multistep_denoise`` (joint_pnp_sci_algo.py:118-306).  One launch per
+    iteration does the projection and ``theta = TV(x - b)`` (:213-230); ``theta`` then goes to
+    ``second_denoiser(theta_dev, nsig, model)`` (:242 / :263) as a CUDA tensor, is clipped to
+    [0, 1] (:268), and the multiplier is formed from it, ``b = b - (x - theta)`` (:270), with
+    the reference's operation order.  Returns ``x`` and the PSNR of ``x`` (:273), like the
+    reference."""
+    if str(denoiser).lower() not in ('tv+ffdnet', 'tv+fastdvdnet'):
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    if tvm not in ('tv_chambolle', 'ITV3D_FGP', 'ITV2D_cham'):      # all three call denoise_tv_chambolle here
+        raise ValueError('Unsupported TV denoiser {}!'.format(tvm))
+    if not multichannel:
+        raise NotImplementedError("multichannel=False is not on the reference's hot path")
+    if second_denoiser is None:
+        raise NotImplementedError(
+            "the learned denoisers of the reference (packages/ffdnet, packages/fastdvdnet) are not part "
+            "of this engine: pass second_denoiser=callable(theta_dev, nsig, model)")
+    Phi = _recover_phi(A, At, y, Phi)
+    yh = f32c(_host(y))
+    Xo = None if X_orig is None else f32c(_host(X_orig))
+    H, W, Cc = Phi.shape
+    if not isinstance(sigma, list):
+        sigma = [sigma]
+    if not isinstance(iter_max, list):
+        iter_max = [iter_max] * len(sigma)
+    psnr_all = []
+    with Solver(1, H, W, Cc, method="admm", _lambda=_lambda, gamma=gamma, tv_weight=tv_weight,
+                tv_iter_max=tv_iter_max, fused=_base.USE_FUSED, clip=False) as s:
+        s.load(yh[None], Phi, Phi_sum=f32c(_host(Phi_sum)),
+               x0=None if x0 is None else f32c(_host(x0))[None])
+        dev = torch.device("cuda", torch.cuda.current_device())
+        Xd = None if (Xo is None or not show_iqa) else torch.from_numpy(Xo).to(dev)
+        shape = (H, W, Cc)
+        for idx, nsig in enumerate(sigma):
+            for _ in range(int(iter_max[idx])):
+                b_old = _wrap(s.admm_state_ptrs()[1], shape, dev).clone()
+                s.run(1)                                   # x, theta = TV(x - b)   (:213-230)
+                tp, bp, xp = s.admm_state_ptrs()           # the buffers ping-pong: ask again
+                theta, b, x = (_wrap(p, shape, dev) for p in (tp, bp, xp))
+                out = second_denoiser(theta, nsig, model)  # :242 / :263
+                if out is not None and out is not theta:
+                    theta.copy_(out.to(dev, torch.float32).reshape(shape))
+                theta.clamp_(0, 1)                          # :268
+                b.copy_(b_old - (x - theta))                # :270 (the launch formed b from the TV output)
+                if Xd is not None:
+                    psnr_all.append(psnr(Xd, x))            # :273
+        x = s.get_x()[0]
+    ps, ss = frames_iqa(Xo, x)
+    return x, ps, ss, psnr_all
+
+
+def admm_joint_denoise(y, Phi_sum, A=None, At=None, x0=None, X_orig=None, denoiser='tv+ffdnet',
+                       iter_max1=50, iter_max2=50, sigma1=None, sigma2=None, **args):
+    """Two periods (joint_pnp_sci_algo.py:81-98): the ADMM-TV above (theta clipped), then
+    ``admm_multistep_denoise`` from its result; returns what the second period returns."""
+    second = args.pop("second_denoiser", None)
+    x, _, _, _ = admm_denoise(y, Phi_sum, A, At, x0=x0, X_orig=X_orig, denoiser='tv',
+                              iter_max=iter_max1, sigma=sigma1, **args)
+    return admm_multistep_denoise(y, Phi_sum, A, At, x0=x, X_orig=X_orig, denoiser=denoiser,
+                                  iter_max=iter_max2, sigma=sigma2, second_denoiser=second, **args)

@@ -117,6 +117,21 @@ def main():
          psnr_all=np.array(pa), iter_max1=4, iter_max2=np.array([2, 2]), sigma2=np.array([0.2, 0.1]),
          tv_weight=0.3, tv_iter_max=5)
 
+    x, ps, ss, pa = ref_joint.admm_multistep_denoise(y, ms, A, At, _lambda=1, gamma=0.01,
+                                                     denoiser='tv+ffdnet', iter_max=[3, 3],
+                                                     sigma=[0.2, 0.1], tv_weight=0.3, tv_iter_max=5,
+                                                     X_orig=Xo)
+    save("joint_admm_multistep", y=y, mask=mask, X_orig=Xo, x=x, psnr=np.array(ps), ssim=np.array(ss),
+         psnr_all=np.array(pa), iter_max=np.array([3, 3]), sigma=np.array([0.2, 0.1]), tv_weight=0.3,
+         tv_iter_max=5, gamma=0.01)
+    x, ps, ss, pa = ref_joint.admm_joint_denoise(y, ms, A, At, X_orig=Xo, denoiser='tv+ffdnet',
+                                                 iter_max1=4, iter_max2=[2, 2], sigma1=None,
+                                                 sigma2=[0.2, 0.1], _lambda=1, gamma=0.01,
+                                                 tv_weight=0.3, tv_iter_max=5)
+    save("joint_admm_two_period", y=y, mask=mask, X_orig=Xo, x=x, psnr=np.array(ps), ssim=np.array(ss),
+         psnr_all=np.array(pa), iter_max1=4, iter_max2=np.array([2, 2]), sigma2=np.array([0.2, 0.1]),
+         tv_weight=0.3, tv_iter_max=5, gamma=0.01)
+
     # warm start + ragged channel count (C=5, odd sizes)
     meas5, mask5, orig5 = cacti(33, 29, 5, 1, cfg=12)
     A5 = lambda x: ref_utils.A_(x, mask5)

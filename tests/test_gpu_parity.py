@@ -569,6 +569,32 @@ def test_joint_multistep_and_two_period_golden(sp, golden, path):
         J.gap_multistep_denoise(g["y"], ms, A, At, denoiser='tv', iter_max=1, second_denoiser=second)
 
 
+def test_joint_admm_multistep_and_two_period_golden(sp, golden, path):
+    """The ADMM twin: the second denoiser sits between the TV step and the multiplier update."""
+    import torch
+    from scipnp import joint_pnp_sci_algo as J
+
+    def second(theta_dev, nsig, model=None):
+        assert theta_dev.is_cuda
+        return torch.clamp(theta_dev * float(np.float32(1.0 - 0.1 * float(nsig))) + float(np.float32(0.01)), 0, 1)
+
+    g = golden("joint_admm_multistep")
+    A, At = _ops(g["mask"])
+    ms = _psum(g["mask"])
+    x, ps, ss, pa = J.admm_multistep_denoise(g["y"], ms, A, At, gamma=0.01, iter_max=[3, 3],
+                                             sigma=[0.2, 0.1], tv_weight=0.3, tv_iter_max=5,
+                                             X_orig=g["X_orig"], second_denoiser=second, tvm='ITV3D_FGP')
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+    g = golden("joint_admm_two_period")
+    x, ps, ss, pa = J.admm_joint_denoise(g["y"], ms, A, At, X_orig=g["X_orig"], iter_max1=4,
+                                         iter_max2=[2, 2], sigma1=None, sigma2=[0.2, 0.1], _lambda=1,
+                                         gamma=0.01, tv_weight=0.3, tv_iter_max=5, second_denoiser=second)
+    assert len(pa) == 4
+    _cmp(x, g["x"], pa, g["psnr_all"], path)
+    with pytest.raises(NotImplementedError):
+        J.admm_multistep_denoise(g["y"], ms, A, At, iter_max=1, sigma=0.1)
+
+
 def test_c_abi_kernel_entries_directly(sp):
     """The stateless C entries called with raw device pointers: one fused iteration equals
     scipnp_gap_project + scipnp_tv_chambolle, and the ADMM pieces compose to the reference update."""

@@ -176,3 +176,21 @@ def test_joint_multistep_and_two_period(golden):
     np.testing.assert_array_equal(np.array(pa), g["psnr_all"])
     with pytest.raises(ValueError):
         O.gap_multistep_denoise(g["y"], ms, A, At, _second_standin, denoiser='tv', iter_max=1)
+
+
+def test_joint_admm_multistep_and_two_period(golden):
+    g = golden("joint_admm_multistep")
+    A, At = _ops(g["mask"])
+    ms = O.phi_sum(g["mask"])
+    x, ps, ss, pa = O.admm_multistep_denoise(g["y"], ms, A, At, _second_standin, gamma=0.01,
+                                             iter_max=[3, 3], sigma=[0.2, 0.1], tv_weight=0.3,
+                                             tv_iter_max=5, X_orig=g["X_orig"])
+    np.testing.assert_array_equal(x, g["x"])
+    np.testing.assert_array_equal(np.array(pa), g["psnr_all"])
+    g = golden("joint_admm_two_period")
+    x, ps, ss, pa = O.admm_joint_denoise(g["y"], ms, A, At, _second_standin, X_orig=g["X_orig"],
+                                         iter_max1=4, iter_max2=[2, 2], sigma1=None, sigma2=[0.2, 0.1],
+                                         _lambda=1, gamma=0.01, tv_weight=0.3, tv_iter_max=5)
+    assert len(pa) == 4
+    np.testing.assert_array_equal(x, g["x"])
+    np.testing.assert_array_equal(np.array(pa), g["psnr_all"])
