@@ -3,4 +3,6 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from scipnp.joint_pnp_sci_algo import admm_denoise, gap_denoise, A_, At_, psnr    # noqa: F401,E402
+from scipnp.joint_pnp_sci_algo import (admm_denoise, gap_denoise, gap_multistep_denoise,     # noqa: F401,E402
+                                       gap_joint_denoise, admm_multistep_denoise, admm_joint_denoise,
+                                       A_, At_, psnr)
