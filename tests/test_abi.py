@@ -78,6 +78,14 @@ def test_no_cpu_fallback_without_device():
         scipnp.gap_denoise(y, m.sum(2), Phi=m, iter_max=1)
     with pytest.raises(scipnp.ScipnpError):
         scipnp.A_(m, m)
+    # the host pipeline and the joint module's hand-off loops fail the same way
+    pl = C.c_void_p()
+    assert lib.scipnp_pipeline_create(C.byref(p), 2, C.byref(pl)) == -2
+    with pytest.raises(scipnp.ScipnpError):
+        scipnp.HostPipeline(1, 8, 8, 4)
+    from scipnp import joint_pnp_sci_algo as J
+    with pytest.raises(scipnp.ScipnpError):
+        J.gap_multistep_denoise(y, m.sum(2), Phi=m, iter_max=1, sigma=0.1, second_denoiser=lambda x, s, mdl: x)
 
 
 def test_argument_validation_happens_before_any_device_work():
@@ -90,6 +98,13 @@ def test_argument_validation_happens_before_any_device_work():
         scipnp.admm_denoise(y, m.sum(2), Phi=m, denoiser='bm3d', iter_max=1)
     with pytest.raises(ValueError):
         scipnp.admmdenoise_cacti(y[..., None], m, projmeth='ista', denoiser='tv')
+    from scipnp import joint_pnp_sci_algo as J
+    with pytest.raises(ValueError):
+        J.gap_multistep_denoise(y, m.sum(2), Phi=m, denoiser='tv', iter_max=1, second_denoiser=lambda x, s, mdl: x)
+    with pytest.raises(ValueError):
+        J.admm_multistep_denoise(y, m.sum(2), Phi=m, tvm='tv_bregman', iter_max=1, second_denoiser=lambda x, s, mdl: x)
+    with pytest.raises(NotImplementedError):      # the learned denoisers are the caller's
+        J.gap_multistep_denoise(y, m.sum(2), Phi=m, iter_max=1)
     with pytest.raises(ValueError):      # opaque operators that are not mask operators
         scipnp.gap_denoise(y, m.sum(2), A=lambda x: x.sum(2) * 2 + 1, At=lambda v: np.ones((8, 8, 4), np.float32),
                            iter_max=1)
