@@ -94,6 +94,16 @@ int scipnp_tv_chambolle(const float *in, float *out, double weight, double eps,
                         int *n_exec_dev, double *energy_dev, int energy_cap,
                         void *stream);
 
+/* Per-frame quality numbers of the solvers' return tuples: compare_psnr / compare_ssim of
+ *     scikit-image < 0.18 as called at pnp_sci_algo.py:699-705 and :857-863 (per channel,
+ *     data_range = 1; SSIM: 7x7 uniform window, sample covariance, K1 = 0.01, K2 = 0.03, mean over
+ *     the pixels whose window lies inside the image).  ref, img: [H][W][C] device arrays.  Writes
+ *     per channel (device, double, C values each) the SUM of the SSIM map over its
+ *     (H-6)*(W-6) inner pixels and the sum of squared errors over H*W pixels:
+ *     ssim = ssim_sum / ((H-6)*(W-6)),  psnr = 10*log10(H*W / sqerr_sum).                 */
+int scipnp_frames_iqa(const float *ref, const float *img, int H, int W, int C,
+                      double *ssim_sum_dev, double *sqerr_sum_dev, void *stream);
+
 /* R10 utils.psnr (utils.py:28-36): accumulates sum((a-b)^2) into *sum_dev
  *     (double, device; the caller zeroes it).  psnr = 10*log10(n/sum).         */
 int scipnp_sq_err(const float *a, const float *b, size_t n, double *sum_dev,

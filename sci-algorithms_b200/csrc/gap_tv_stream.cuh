@@ -479,7 +479,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     // stage 0 of step rho (row j of the block in `buf`): f(rho) = x + (lambda*s) * Phi for this warp's chunk
     // ROWS_OK: the caller guarantees r0 <= rho < r1 (no row predicate on the stores)
     auto project_row = [&](const unsigned char* buf, const float* sbuf, int j, int rho, long long xoff, auto rows_ok, P2 (&f_new)[2]) {
-        constexpr bool ROWS_OK = decltype(rows_ok)::value;
+        [[maybe_unused]] constexpr bool ROWS_OK = decltype(rows_ok)::value;      // used by the ADMM store only
         const float4* tx = reinterpret_cast<const float4*>(buf) + chunk_idx(gi, k, j, lane);
         const float4 xv = tx[0], pv = load_phi(tx, rho, px, px_in, k);
         const P2 s2 = splat(sbuf[(j * NG + gi) * 32 + lane]);

@@ -403,6 +403,92 @@ int scipnp_sq_err(const float* a, const float* b, size_t n, double* sum_dev, voi
     return launch_sq_err(a, b, n, 1, sum_dev, (cudaStream_t)stream);
 }
 
+// ---- per-frame image quality of the return tuples ---------------------------------------------
+// compare_psnr / compare_ssim of scikit-image < 0.18 as the reference calls them
+// (pnp_sci_algo.py:699-705, 857-863: per channel, data_range = 1): SSIM with a 7x7 uniform window,
+// sample covariance (cov_norm = 49/48), K1 = 0.01, K2 = 0.03, averaged over the pixels whose window
+// lies inside the image; squared error in float32, summed in double.  Arithmetic in double like
+// skimage (inputs are converted to float64 there).
+namespace {
+
+constexpr int kIqaWin = 7, kIqaPad = 3, kIqaSeg = 64;
+
+__global__ void __launch_bounds__(128) frames_iqa_kernel(const float* __restrict__ ref, const float* __restrict__ img,
+                                                         int H, int W, int C, double* __restrict__ ssim_sum,
+                                                         double* __restrict__ sqerr_sum) {
+    extern __shared__ double sacc[];                   // [2][C]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.0;
+    __syncthreads();
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (w, c), c fastest
+    const bool valid = j < (long long)W * C;
+    const int w = valid ? (int)(j / C) : 0, c = valid ? (int)(j - (long long)w * C) : 0;
+    const int h0 = blockIdx.y * kIqaSeg, h1 = min(H, h0 + kIqaSeg);
+    double ss = 0.0, se = 0.0;
+    if (valid) {
+        for (int h = h0; h < h1; ++h) {                // squared error: every pixel
+            const size_t o = ((size_t)h * W + w) * C + c;
+            const float d = ref[o] - img[o];
+            se += (double)(d * d);
+        }
+        const bool inner = w >= kIqaPad && w < W - kIqaPad;
+        const int c0 = max(h0, kIqaPad), c1 = min(h1, H - kIqaPad);           // window centres of this segment
+        if (inner && c1 > c0) {
+            double rx[kIqaWin], ry[kIqaWin], rxx[kIqaWin], ryy[kIqaWin], rxy[kIqaWin];   // row sums of the last 7 rows
+#pragma unroll
+            for (int i = 0; i < kIqaWin; ++i) rx[i] = ry[i] = rxx[i] = ryy[i] = rxy[i] = 0.0;
+            for (int r = c0 - kIqaPad; r < c1 + kIqaPad; ++r) {
+                double hx = 0, hy = 0, hxx = 0, hyy = 0, hxy = 0;
+#pragma unroll
+                for (int d = -kIqaPad; d <= kIqaPad; ++d) {
+                    const size_t o = ((size_t)r * W + (w + d)) * C + c;
+                    const double a = (double)ref[o], b = (double)img[o];
+                    hx += a; hy += b; hxx += a * a; hyy += b * b; hxy += a * b;
+                }
+#pragma unroll
+                for (int i = 0; i < kIqaWin - 1; ++i) {
+                    rx[i] = rx[i + 1]; ry[i] = ry[i + 1]; rxx[i] = rxx[i + 1]; ryy[i] = ryy[i + 1]; rxy[i] = rxy[i + 1];
+                }
+                rx[kIqaWin - 1] = hx; ry[kIqaWin - 1] = hy; rxx[kIqaWin - 1] = hxx; ryy[kIqaWin - 1] = hyy; rxy[kIqaWin - 1] = hxy;
+                if (r >= c0 + kIqaPad) {               // the window centred on row r-3 is complete
+                    double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+#pragma unroll
+                    for (int i = 0; i < kIqaWin; ++i) { sx += rx[i]; sy += ry[i]; sxx += rxx[i]; syy += ryy[i]; sxy += rxy[i]; }
+                    const double inv = 1.0 / (kIqaWin * kIqaWin), cn = 49.0 / 48.0;
+                    const double ux = sx * inv, uy = sy * inv;
+                    const double vx = cn * (sxx * inv - ux * ux), vy = cn * (syy * inv - uy * uy);
+                    const double vxy = cn * (sxy * inv - ux * uy);
+                    const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03;
+                    ss += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+                }
+            }
+        }
+        atomicAdd(&sacc[c], ss);
+        atomicAdd(&sacc[C + c], se);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        if (sacc[i] != 0.0) atomicAdd(ssim_sum + i, sacc[i]);
+        if (sacc[C + i] != 0.0) atomicAdd(sqerr_sum + i, sacc[C + i]);
+    }
+}
+
+}  // namespace
+
+int scipnp_frames_iqa(const float* ref, const float* img, int H, int W, int C, double* ssim_sum_dev,
+                      double* sqerr_sum_dev, void* stream) {
+    if (int e = check_dims(1, H, W, C)) return e;
+    SCIPNP_REQUIRE(ref && img && ssim_sum_dev && sqerr_sum_dev, "null pointer");
+    SCIPNP_REQUIRE(H >= kIqaWin && W >= kIqaWin, "win_size exceeds image extent (7x7 SSIM window)");
+    SCIPNP_REQUIRE(C <= 4096, "too many channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    SCIPNP_CUDA(cudaMemsetAsync(ssim_sum_dev, 0, C * sizeof(double), st));
+    SCIPNP_CUDA(cudaMemsetAsync(sqerr_sum_dev, 0, C * sizeof(double), st));
+    dim3 grid((unsigned)ceil_div_ll((long long)W * C, 128), (unsigned)ceil_div_ll(H, kIqaSeg), 1);
+    frames_iqa_kernel<<<grid, 128, 2 * C * sizeof(double), st>>>(ref, img, H, W, C, ssim_sum_dev, sqerr_sum_dev);
+    count_launch();
+    return check_launch("frames_iqa_kernel");
+}
+
 int scipnp_bayer_split(const float* full, float* quad, int H, int W, int C, void* stream) {
     if (int e = check_dims(1, H, W, C)) return e;
     SCIPNP_REQUIRE(full && quad, "null pointer");

@@ -1,40 +1,55 @@
 """Per-frame image-quality numbers of the solvers' return tuples
 (``compare_psnr`` / ``compare_ssim`` of scikit-image < 0.18, called at
-pnp_sci_algo.py:699-705, 857-863).  Computed once per reconstruction on the
-final frames, on the host: off the hot path.
+pnp_sci_algo.py:699-705, 857-863), computed on the device by
+``scipnp_frames_iqa``: once per reconstruction on the
+final frames, off the timed path.  Inputs may be host arrays (uploaded) or CUDA
+tensors.
 """
+import math
+
 import numpy as np
-from scipy.ndimage import uniform_filter
+import torch
+
+from ._lib import lib, check
+from .engine import to_device, stream_ptr, dptr
 
 __all__ = ["frame_psnr", "frame_ssim", "frames_iqa"]
 
 
+def _iqa(ref, img):
+    a, b = to_device(ref), to_device(img)
+    if a.shape != b.shape or a.dim() not in (2, 3):
+        raise ValueError("frames_iqa expects two [H, W] or [H, W, C] arrays of equal shape")
+    if a.dim() == 2:
+        a, b = a[..., None], b[..., None]
+    H, W, Cc = a.shape
+    if H < 7 or W < 7:
+        raise ValueError("win_size exceeds image extent.")          # skimage's message for the 7x7 window
+    a, b = a.contiguous(), b.contiguous()
+    acc = torch.empty((2, Cc), dtype=torch.float64, device=a.device)
+    check(lib.scipnp_frames_iqa(dptr(a), dptr(b), H, W, Cc, dptr(acc[0]), dptr(acc[1]), stream_ptr()))
+    s = acc.cpu().numpy()
+    ssim = s[0] / float((H - 6) * (W - 6))
+    mse = s[1] / float(H * W)
+    with np.errstate(divide="ignore"):
+        psnr = 10 * np.log10(1.0 / mse)                             # data_range = 1
+    return [float(v) for v in psnr], [float(v) for v in ssim]
+
+
 def frame_psnr(ref, img, data_range=1.):
-    ref = np.asarray(ref, dtype=np.float32)
-    img = np.asarray(img, dtype=np.float32)
-    mse = np.mean((ref - img) ** 2, dtype=np.float64)
-    return 10 * np.log10((data_range ** 2) / mse)
+    if data_range != 1.:
+        raise NotImplementedError("the reference calls compare_psnr with data_range=1.")
+    return _iqa(ref, img)[0][0]
 
 
 def frame_ssim(ref, img, data_range=1., win=7):
-    X = np.asarray(ref, dtype=np.float64)
-    Y = np.asarray(img, dtype=np.float64)
-    n = win ** X.ndim
-    cn = n / (n - 1.)
-    mx, my = uniform_filter(X, win), uniform_filter(Y, win)
-    vx = cn * (uniform_filter(X * X, win) - mx * mx)
-    vy = cn * (uniform_filter(Y * Y, win) - my * my)
-    vxy = cn * (uniform_filter(X * Y, win) - mx * my)
-    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
-    S = ((2 * mx * my + c1) * (2 * vxy + c2)) / ((mx * mx + my * my + c1) * (vx + vy + c2))
-    pad = (win - 1) // 2
-    return float(S[tuple(slice(pad, d - pad) for d in S.shape)].mean())
+    if data_range != 1. or win != 7:
+        raise NotImplementedError("the reference calls compare_ssim with data_range=1. and the default window")
+    return _iqa(ref, img)[1][0]
 
 
 def frames_iqa(X_orig, x):
     """(psnr_, ssim_) lists over the last axis, or two empty lists."""
     if X_orig is None:
         return [], []
-    ps = [frame_psnr(X_orig[..., c], x[..., c]) for c in range(x.shape[-1])]
-    ss = [frame_ssim(X_orig[..., c], x[..., c]) for c in range(x.shape[-1])]
-    return ps, ss
+    return _iqa(X_orig, x)

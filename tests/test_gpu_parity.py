@@ -595,6 +595,27 @@ def test_joint_admm_multistep_and_two_period_golden(sp, golden, path):
         J.admm_multistep_denoise(g["y"], ms, A, At, iter_max=1, sigma=0.1)
 
 
+@pytest.mark.parametrize("shape", [(40, 48, 8), (7, 7, 1), (9, 133, 3), (130, 11, 5)])
+def test_frames_iqa_matches_skimage_restatement(sp, shape):
+    """per-frame PSNR / SSIM of the return tuples on the device
+    (scipnp_frames_iqa) against the oracle's compare_psnr / compare_ssim (skimage 0.17.2)."""
+    from oracle import iqa as OI
+    from scipnp.iqa import frames_iqa, frame_ssim
+    rng = np.random.default_rng(5)
+    H, W, Cc = shape
+    ref = rng.random(shape, dtype=np.float32)
+    img = np.clip(ref + np.float32(0.05) * rng.standard_normal(shape).astype(np.float32), 0, 1)
+    img[..., 0] = ref[..., 0] * np.float32(0.5)                  # a very different frame too
+    ps, ss = frames_iqa(ref, img)
+    for c in range(Cc):
+        assert abs(ps[c] - OI.compare_psnr(ref[..., c], img[..., c], data_range=1.)) <= 1e-9
+        assert abs(ss[c] - OI.compare_ssim(ref[..., c], img[..., c], data_range=1.)) <= 1e-10
+    assert frame_ssim(ref[..., 0], ref[..., 0]) == pytest.approx(1.0, abs=1e-12)
+    assert frames_iqa(None, img) == ([], [])
+    with pytest.raises(ValueError):
+        frames_iqa(ref[:6], img[:6])                              # smaller than the 7x7 window
+
+
 def test_c_abi_kernel_entries_directly(sp):
     """The stateless C entries called with raw device pointers: one fused iteration equals
     scipnp_gap_project + scipnp_tv_chambolle, and the ADMM pieces compose to the reference update."""
