@@ -94,6 +94,14 @@ int scipnp_tv_chambolle(const float *in, float *out, double weight, double eps,
                         int *n_exec_dev, double *energy_dev, int energy_cap,
                         void *stream);
 
+/* MATLAB twin's default TV denoiser (PnP_SCI/matlab/algorithms/tvdenoisers/TV_denoising.m:1-44,
+ *     the 'ATV_ClipA' branch of gapdenoise.m:93-94): anisotropic TV by iterative clipping,
+ *     alpha = 5, per 2-D frame of a [B][H][W][C] stack; `iters` iterations, the x of the last one
+ *     is returned.  workspace: scipnp_tv_atv_clip_workspace_bytes (the two dual fields).       */
+size_t scipnp_tv_atv_clip_workspace_bytes(int B, int H, int W, int C);
+int scipnp_tv_atv_clip(const float *in, float *out, float lambda, int iters, int B, int H, int W,
+                       int C, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Per-frame quality numbers of the solvers' return tuples: compare_psnr / compare_ssim of
  *     scikit-image < 0.18 as called at pnp_sci_algo.py:699-705 and :857-863 (per channel,
  *     data_range = 1; SSIM: 7x7 uniform window, sample covariance, K1 = 0.01, K2 = 0.03, mean over

@@ -23,4 +23,12 @@ Parity status
   one function is **parity unpinned**; it is corroborated (interior pixels, to
   1e-15 in float64) by a transliteration of the in-tree MATLAB
   ``tvdenoise_cham_ITV2D.m`` (``tests/test_oracle_tv.py``).
+* Joint module: ``joint_admm_denoise``, ``gap_multistep_denoise``,
+  ``admm_multistep_denoise``, ``gap_joint_denoise``, ``admm_joint_denoise`` in
+  ``oracle/pnp_sci.py``: PINNED against ``joint_pnp_sci_algo.py`` run unmodified, a fixed
+  elementwise stand-in injected in FFDNet's place for the TV+CNN periods.
+* IQA (``oracle/iqa.py``: ``compare_psnr``, ``compare_ssim`` of scikit-image 0.17.2) and the
+  MATLAB twin's ``TV_denoising.m`` (``oracle/matlab_tv.py``): restated from the published /
+  in-tree sources, **parity unpinned** (scikit-image, MATLAB and Octave are absent here);
+  checked by properties in ``tests/``.
 """

@@ -275,3 +275,90 @@ int scipnp_tv_chambolle(const float* in, float* out, double weight, double eps, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// MATLAB twin's default TV: anisotropic TV by iterative clipping, per 2-D frame,
+// PnP_SCI/matlab/algorithms/tvdenoisers/TV_denoising.m:1-44 (the 'ATV_ClipA' branch of
+// gapdenoise.m:93-94).  alpha = 5; per iteration
+//     x0 = ((y0 - dht(zh)) + (y0 - dvt(zv))) / 2                      (:26-28)
+//     zh = clip(zh + (1/alpha) dh(x0), lambda/2),  zv likewise         (:29-30)
+// with dh/dv forward differences and dht/dvt their transposes (:51-64); the x0 of the last
+// iteration is returned, so the last z update is dead.  IEEE single precision in the statement
+// order of the .m file (a float32 NumPy restatement is reproduced bit for bit).
+// ---------------------------------------------------------------------------------------------
+namespace scipnp {
+namespace {
+
+// zh, zv: [B][H][W][C]; column W-1 of zh and row H-1 of zv are never read
+__global__ void atv_x_kernel(const float* __restrict__ y0, const float* __restrict__ zh, const float* __restrict__ zv,
+                             float* __restrict__ x0, int H, int W, int C, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t pix = i / C;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H);
+    const size_t sw = (size_t)C, sh = (size_t)W * C;
+    float dht, dvt;                                    // TV_denoising.m:57-58, :53-54
+    if (w == 0) dht = -zh[i];
+    else if (w == W - 1) dht = zh[i - sw];
+    else dht = -__fsub_rn(zh[i], zh[i - sw]);
+    if (h == 0) dvt = -zv[i];
+    else if (h == H - 1) dvt = zv[i - sh];
+    else dvt = -__fsub_rn(zv[i], zv[i - sh]);
+    const float v = y0[i];
+    x0[i] = __fmul_rn(__fadd_rn(__fsub_rn(v, dht), __fsub_rn(v, dvt)), 0.5f);
+}
+
+__device__ __forceinline__ float atv_clip(float v, float t) {      // :67-68  sign(x).*min(abs(x), t)
+    const float m = fminf(fabsf(v), t);
+    return v > 0.f ? m : (v < 0.f ? -m : 0.f * m);
+}
+
+__global__ void atv_z_kernel(const float* __restrict__ x0, float* __restrict__ zh, float* __restrict__ zv,
+                             float inv_alpha, float half_lambda, int H, int W, int C, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t pix = i / C;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H);
+    const size_t sw = (size_t)C, sh = (size_t)W * C;
+    const float v = x0[i];
+    if (w < W - 1) zh[i] = atv_clip(__fadd_rn(zh[i], __fmul_rn(inv_alpha, __fsub_rn(x0[i + sw], v))), half_lambda);
+    if (h < H - 1) zv[i] = atv_clip(__fadd_rn(zv[i], __fmul_rn(inv_alpha, __fsub_rn(x0[i + sh], v))), half_lambda);
+}
+
+}  // namespace
+}  // namespace scipnp
+
+extern "C" {
+
+size_t scipnp_tv_atv_clip_workspace_bytes(int B, int H, int W, int C) {
+    if (B < 1 || H < 1 || W < 1 || C < 1) return 0;
+    return 2 * (size_t)B * H * W * C * sizeof(float);
+}
+
+int scipnp_tv_atv_clip(const float* in, float* out, float lambda, int iters, int B, int H, int W, int C,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace scipnp;
+    SCIPNP_REQUIRE(B >= 1 && H >= 2 && W >= 2 && C >= 1, "bad dimensions (frames must be at least 2x2)");
+    SCIPNP_REQUIRE(in && out && workspace, "null pointer");
+    SCIPNP_REQUIRE(in != out, "in and out must not alias");
+    SCIPNP_REQUIRE(iters >= 1, "iters must be >= 1");
+    const size_t n = (size_t)B * H * W * C;
+    if (workspace_bytes < 2 * n * sizeof(float)) { set_error("ATV workspace too small"); return SCIPNP_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* zh = reinterpret_cast<float*>(workspace);
+    float* zv = zh + n;
+    SCIPNP_CUDA(cudaMemsetAsync(zh, 0, 2 * n * sizeof(float), st));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const float inv_alpha = (float)(1.0 / 5.0), half = (float)((double)lambda / 2.0);
+    for (int it = 0; it < iters; ++it) {
+        atv_x_kernel<<<blocks, 256, 0, st>>>(in, zh, zv, out, H, W, C, n);
+        count_launch();
+        if (it + 1 < iters) {
+            atv_z_kernel<<<blocks, 256, 0, st>>>(out, zh, zv, inv_alpha, half, H, W, C, n);
+            count_launch();
+        }
+    }
+    return check_launch("atv kernels");
+}
+
+}  // extern "C"

@@ -616,6 +616,52 @@ def test_frames_iqa_matches_skimage_restatement(sp, shape):
         frames_iqa(ref[:6], img[:6])                              # smaller than the 7x7 window
 
 
+@pytest.mark.parametrize("shape,iters", [((2, 2, 1), 3), ((17, 23, 5), 1), ((17, 23, 5), 5), ((40, 48, 8), 20)])
+def test_matlab_tv_atv_clip_bit_exact(sp, shape, iters):
+    """TV_denoising.m (the MATLAB twin's default TV, anisotropic, iterative clipping)
+    on the device against its float32 NumPy restatement, bit for bit."""
+    from oracle import matlab_tv as M
+    from scipnp import matlab_tv as G
+    rng = np.random.default_rng(11)
+    y = rng.random(shape, dtype=np.float32)
+    for lam in (0.07, 0.5):
+        np.testing.assert_array_equal(G.TV_denoising(y, lam, iters), M.TV_denoising(y, lam, iters))
+    np.testing.assert_array_equal(G.TV_denoising(y[:, :, 0], 0.2, iters), M.TV_denoising(y[:, :, 0], 0.2, iters))
+    with pytest.raises(ValueError):
+        G.TV_denoising(y[:1], 0.1, 2)
+
+
+def test_matlab_gapdenoise_loop(sp, golden):
+    """gapdenoise.m:62-94 with tvm = 'ATV_ClipA': the device loop against the same loop written
+    with the oracle's operators and TV restatement (Phisum = sum(mask.^2), as the MATLAB drivers do)."""
+    from oracle import matlab_tv as M
+    from oracle import pnp_sci as O
+    from scipnp import matlab_tv as G
+    g = golden("gap_acc")
+    mask, y, Xo = g["mask"], g["y"], g["X_orig"]
+    Phisum = np.sum(mask * mask, axis=2)
+    Phisum[Phisum == 0] = 1
+    f32 = np.float32
+    for acc in (True, False):
+        v = O.At_(y, mask)
+        y1 = np.zeros_like(y)
+        want_psnr = []
+        for _ in range(6):
+            yb = O.A_(v, mask)
+            if acc:
+                y1 = y1 + (y - yb)
+                v = v + f32(0.2) * O.At_((y1 - yb) / Phisum, mask)
+            else:
+                v = v + f32(0.2) * O.At_((y - yb) / Phisum, mask)
+            v = M.TV_denoising(v, 0.07, 5)
+            want_psnr.append(O.psnr(Xo, v))
+        got, pa = G.gapdenoise(y, mask, lambda_=0.2, maxiter=6, acc=acc, tvweight=0.07, tviter=5, orig=Xo)
+        assert np.abs(got - v).max() <= TOL_EXACT
+        assert np.abs(np.array(pa) - np.array(want_psnr)).max() <= TOL_DB
+    with pytest.raises(ValueError):
+        G.gapdenoise(y, mask, tvm='ITV2D_cham', maxiter=1)
+
+
 def test_c_abi_kernel_entries_directly(sp):
     """The stateless C entries called with raw device pointers: one fused iteration equals
     scipnp_gap_project + scipnp_tv_chambolle, and the ADMM pieces compose to the reference update."""

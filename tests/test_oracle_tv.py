@@ -100,3 +100,44 @@ def test_rof_objective_decreases():
 def test_float32_dtype_preserved():
     f = np.random.default_rng(4).random((6, 6, 2)).astype(np.float32)
     assert denoise_tv_chambolle(f, 0.1, n_iter_max=3, multichannel=True).dtype == np.float32
+
+
+# -- MATLAB twin's default TV: oracle/matlab_tv.py, property checks -----------------
+
+def _frames(shape, seed=3, dtype=np.float32):
+    rng = np.random.default_rng(seed)
+    return rng.random(shape).astype(dtype)
+
+
+def test_matlab_tv_adjoint_pairs():
+    from oracle import matlab_tv as M
+    x = _frames((9, 11, 3), dtype=np.float64)
+    zh = _frames((9, 10, 3), 4, np.float64)
+    zv = _frames((8, 11, 3), 5, np.float64)
+    assert abs(np.sum(M.dh(x) * zh) - np.sum(x * M.dht(zh))) < 1e-10       # TV_denoising.m:55-64
+    assert abs(np.sum(M.dv(x) * zv) - np.sum(x * M.dvt(zv))) < 1e-10
+
+
+@pytest.mark.parametrize("iters", [1, 5, 30])
+def test_matlab_tv_properties(iters):
+    from oracle import matlab_tv as M
+    y = _frames((13, 10, 4), dtype=np.float64)
+    out = M.TV_denoising(y, 0.2, iters)
+    assert out.shape == y.shape and out.dtype == y.dtype
+    np.testing.assert_allclose(out.mean(axis=(0, 1)), y.mean(axis=(0, 1)), atol=1e-12)   # sum(dht z) = 0
+    const = np.full((6, 7, 2), 0.3)
+    np.testing.assert_array_equal(M.TV_denoising(const, 0.5, iters), const)             # fixed point
+    np.testing.assert_allclose(M.TV_denoising(y, 0.0, iters), y, atol=0)                 # lambda = 0
+    one = M.TV_denoising(y[:, :, 2], 0.2, iters)                                         # frames are independent
+    np.testing.assert_array_equal(one, out[:, :, 2])
+    if iters > 1:                                                                        # it does smooth
+        tv = lambda a: np.abs(np.diff(a, axis=0)).sum() + np.abs(np.diff(a, axis=1)).sum()
+        assert tv(out) < tv(y)
+
+
+def test_matlab_tv_keeps_single_precision():
+    from oracle import matlab_tv as M
+    y = _frames((8, 8, 2))
+    assert M.TV_denoising(y, 0.1, 5).dtype == np.float32
+    with pytest.raises(ValueError):
+        M.TV_denoising(y[:1], 0.1, 5)
