@@ -70,11 +70,20 @@ __global__ void phi_sum_kernel(const float* __restrict__ Phi, float* __restrict_
     int b = blockIdx.y;
     if (p >= npix) return;
     const float* pp = Phi + ((size_t)b * npix + p) * C;
+    const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(Phi) & 15u) == 0;
     float v[kMaxLocalC];
     float acc = 0.f;
     for (int c0 = 0; c0 < C; c0 += kMaxLocalC) {
         int n = min(kMaxLocalC, C - c0);
-        for (int c = 0; c < n; ++c) v[c] = pp[c0 + c];
+        if (vec) {
+            const float4* p4 = reinterpret_cast<const float4*>(pp + c0);
+            for (int c = 0; c < n / 4; ++c) {
+                const float4 t = p4[c];
+                v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+            }
+        } else {
+            for (int c = 0; c < n; ++c) v[c] = pp[c0 + c];
+        }
         float s = numpy_sum(v, n, 1);
         acc = (c0 == 0) ? s : __fadd_rn(acc, s);
     }
@@ -88,6 +97,17 @@ __global__ void At_kernel(const float* __restrict__ y, const float* __restrict__
     if (e >= nelem) return;
     long long p = e / C;
     x[(size_t)b * nelem + e] = __fmul_rn(y[(size_t)b * (nelem / C) + p], Phi[(size_t)b * phi_stride + e]);
+}
+
+// C % 4 == 0 and 16-byte aligned stacks: four channels of one pixel per thread
+__global__ void At_kernel_v4(const float* __restrict__ y, const float4* __restrict__ Phi,
+                             float4* __restrict__ x, long long nelem4, int C4, long long phi_stride4) {
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int b = blockIdx.y;
+    if (e >= nelem4) return;
+    const float yv = y[(size_t)b * (nelem4 / C4) + e / C4];
+    const float4 m = Phi[(size_t)b * phi_stride4 + e];
+    x[(size_t)b * nelem4 + e] = make_float4(__fmul_rn(yv, m.x), __fmul_rn(yv, m.y), __fmul_rn(yv, m.z), __fmul_rn(yv, m.w));
 }
 
 // ---------------------------------------------------------------------------
@@ -353,6 +373,15 @@ int scipnp_At(const float* y, const float* Phi, float* x, int B, int H, int W, i
     if (int e = check_dims(B, H, W, C)) return e;
     SCIPNP_REQUIRE(x && Phi && y, "null pointer");
     long long nelem = (long long)H * W * C;
+    if ((C & 3) == 0 && aligned16(Phi) && aligned16(x)) {
+        const long long n4 = nelem / 4;
+        dim3 grid4((unsigned)ceil_div_ll(n4, 256), B);
+        At_kernel_v4<<<grid4, 256, 0, (cudaStream_t)stream>>>(y, reinterpret_cast<const float4*>(Phi),
+                                                               reinterpret_cast<float4*>(x), n4, C / 4,
+                                                               phi_batched ? n4 : 0);
+        count_launch();
+        return check_launch("At_kernel_v4");
+    }
     dim3 grid((unsigned)ceil_div_ll(nelem, 256), B);
     At_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, Phi, x, nelem, C, phi_batched ? nelem : 0);
     count_launch();

@@ -40,6 +40,8 @@ struct scipnp_solver {
     int* flags = nullptr;      // [1]
     // host state
     bool loaded = false, has_orig = false, use_fused = false;
+    bool x0_given = false;     // load() got an initial guess (else x0 = At(y) can be recomputed)
+    bool snap_valid = false;   // begin() took a snapshot (else the run started from the load state)
     int iters_done = 0, psnr_count = 0, refined = 0, begin_iter = 0;
     bool fused_possible = false;
     // CASSI: coded aperture [H][mask_w]; the fused kernel reads it at per-band offsets
@@ -176,6 +178,7 @@ int scipnp_solver_load(scipnp_solver* s, const float* y, const float* Phi, const
     } else {
         if (int e = scipnp_At(s->y, s->Phi, s->xa, p.B, p.H, p.W, p.C, p.phi_batched, stream)) return e;
     }
+    s->x0_given = x0 != nullptr;
     s->has_orig = X_orig != nullptr;
     if (X_orig) SCIPNP_CUDA(cudaMemcpyAsync(s->Xorig, X_orig, s->n_frame * sizeof(float), cudaMemcpyDefault, st));
     if (p.method == 0) {
@@ -286,9 +289,14 @@ int scipnp_solver_begin(scipnp_solver* s, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     s->begin_iter = s->iters_done;
     if (!s->xsnap) return SCIPNP_OK;          // handle created without the fused path: nothing to roll back
-    SCIPNP_CUDA(cudaMemcpyAsync(s->xsnap, s->xa, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (s->p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1snap, s->y1a, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    else SCIPNP_CUDA(cudaMemcpyAsync(s->bsnap, s->ba, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // A run that starts right after load() with the default initial guess needs no snapshot: a
+    // rollback recomputes x0 = At(y) and clears y1 / b (saves copying the state per reconstruction).
+    s->snap_valid = !(s->iters_done == 0 && !s->x0_given && !s->cassi);
+    if (s->snap_valid) {
+        SCIPNP_CUDA(cudaMemcpyAsync(s->xsnap, s->xa, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (s->p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1snap, s->y1a, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        else SCIPNP_CUDA(cudaMemcpyAsync(s->bsnap, s->ba, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
     SCIPNP_CUDA(cudaMemsetAsync(s->flags, 0, 4 * sizeof(int), st));
     return SCIPNP_OK;
 }
@@ -323,9 +331,19 @@ int scipnp_solver_rollback(scipnp_solver* s, void* stream) {
     if (!s->xsnap) { set_error("this handle keeps no snapshot (created with fused = 0)"); return SCIPNP_ESTATE; }
     cudaStream_t st = (cudaStream_t)stream;
     const scipnp_params& p = s->p;
-    SCIPNP_CUDA(cudaMemcpyAsync(s->xa, s->xsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1a, s->y1snap, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    else SCIPNP_CUDA(cudaMemcpyAsync(s->ba, s->bsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (s->snap_valid) {
+        SCIPNP_CUDA(cudaMemcpyAsync(s->xa, s->xsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1a, s->y1snap, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        else SCIPNP_CUDA(cudaMemcpyAsync(s->ba, s->bsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {                                   // the load state (scipnp_solver_load)
+        if (int e = scipnp_At(s->y, s->Phi, s->xa, p.B, p.H, p.W, p.C, p.phi_batched, stream)) return e;
+        if (p.method == 0) {
+            SCIPNP_CUDA(cudaMemsetAsync(s->y1a, 0, s->n_meas * sizeof(float), st));
+        } else {
+            SCIPNP_CUDA(cudaMemsetAsync(s->ba, 0, s->n_frame * sizeof(float), st));
+            SCIPNP_CUDA(cudaMemcpyAsync(s->xproj, s->xa, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+    }
     const int k0 = s->begin_iter, capi = kPsnrCap / p.B;
     const int n = s->iters_done - k0 < capi - k0 ? s->iters_done - k0 : (capi - k0 > 0 ? capi - k0 : 0);
     if (n > 0) SCIPNP_CUDA(cudaMemsetAsync(s->sqerr + (size_t)k0 * p.B, 0, (size_t)n * p.B * sizeof(double), st));
