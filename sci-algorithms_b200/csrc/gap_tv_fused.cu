@@ -113,6 +113,7 @@ bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max) {
     if (C % 4 != 0 || C / 4 > kMaxWarps) return false;
     if (tv_iter_max < 3 || tv_iter_max > 5) return false;      // R = 2..4 are instantiated
     if (B < 1 || B > 65535 || H < 1 || W < 1) return false;
+    if ((long long)H * W * C >= (1LL << 31)) return false;      // the kernel keeps 32-bit element offsets per frame
     return true;
 }
 

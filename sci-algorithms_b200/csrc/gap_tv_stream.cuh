@@ -284,7 +284,6 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     const long long unit_end = min(total, unit + per_cta);
     int gb = 0;                                  // running block counter: ring slot and mbarrier phase
     const uint32_t pa_bar = bar_base + NSLOT * 8;
-    uint32_t pa_ctr = 0;                         // completed phase-A waits (parity of pa_bar)
     // the y / y1 / Phi_sum rows staged by cp.async need the full barrier for visibility
     const bool split = SPLIT && p.small_tma;
 #pragma unroll 1
@@ -473,12 +472,14 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     // Output cursors of this thread: element offsets of (row 0, px, channel 4k) in a frame and of
     // (row 0, px) in a measurement plane.  Rows are added per block (FAST: once per RB rows), so the
     // steady state carries no 64-bit multiplies.  Never dereferenced for pixels outside the image.
-    const long long xstride = (long long)W * C;
-    const long long xoff0 = (long long)frame_b + (long long)px * C + 4 * k;
+    // (32-bit: launch_fused keeps H*W*C below 2^31; the batch offset sits in the base pointers)
+    const int xstride = W * C;
+    const int xoff0 = px * C + 4 * k;
+    float* const xo_b = p.x_out + frame_b;
 
     // stage 0 of step rho (row j of the block in `buf`): f(rho) = x + (lambda*s) * Phi for this warp's chunk
     // ROWS_OK: the caller guarantees r0 <= rho < r1 (no row predicate on the stores)
-    auto project_row = [&](const unsigned char* buf, const float* sbuf, int j, int rho, long long xoff, auto rows_ok, P2 (&f_new)[2]) {
+    auto project_row = [&](const unsigned char* buf, const float* sbuf, int j, int rho, int xoff, auto rows_ok, P2 (&f_new)[2]) {
         [[maybe_unused]] constexpr bool ROWS_OK = decltype(rows_ok)::value;      // used by the ADMM store only
         const float4* tx = reinterpret_cast<const float4*>(buf) + chunk_idx(gi, k, j, lane);
         const float4 xv = tx[0], pv = load_phi(tx, rho, px, px_in, k);
@@ -488,7 +489,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         if constexpr (MODE == MODE_ADMM) {
             // f = x - b = theta + lambda*s*Phi is the TV input; x = f + b is what admm_denoise returns
             if (own_px && (ROWS_OK || (rho >= r0 && rho < r1))) {
-                const long long o = xoff;
+                const size_t o = frame_b + (long long)xoff;
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(cp.b_in + o));
                 *reinterpret_cast<float4*>(cp.xproj + o) =
                     make_float4(f_new[0].x + bv.x, f_new[0].y + bv.y, f_new[1].x + bv.z, f_new[1].y + bv.w);
@@ -497,7 +498,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     };
     // f_out = f(orow), the value that left the f delay line in this step: the ADMM multiplier update
     // b - (x - theta_new) equals theta_new - f  (pnp_sci_algo.py:836 with x = f + b)
-    auto store_row = [&](int orow, long long xoff, auto rows_ok, const P2 (&oo)[2], const P2 (&f_out)[2]) {
+    auto store_row = [&](int orow, int xoff, auto rows_ok, const P2 (&oo)[2], const P2 (&f_out)[2]) {
         constexpr bool ROWS_OK = decltype(rows_ok)::value;
         if (own_px && (ROWS_OK || (orow >= r0 && orow < r1))) {
             P2 o[2] = {oo[0], oo[1]};
@@ -507,9 +508,9 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
                     for (int q = 0; q < 2; ++q) { o[q].x = fminf(fmaxf(o[q].x, 0.f), 1.f); o[q].y = fminf(fmaxf(o[q].y, 0.f), 1.f); }
                 }
             }
-            *reinterpret_cast<float4*>(p.x_out + xoff) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+            *reinterpret_cast<float4*>(xo_b + xoff) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
             if constexpr (MODE == MODE_ADMM)
-                *reinterpret_cast<float4*>(cp.b_out + xoff) =
+                *reinterpret_cast<float4*>(cp.b_out + frame_b + (long long)xoff) =
                     make_float4(o[0].x - f_out[0].x, o[0].y - f_out[0].y, o[1].x - f_out[1].x, o[1].y - f_out[1].y);
         }
     };
@@ -519,12 +520,14 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         __syncwarp();
         if (lane == 0) mbar_arrive(pa_bar);
     };
-    int rot = gb % NW;
+    {
+    const int rot = gb % NW;
     issue(0, rot);
     issue(1, rot);
     wait_block(0);
     if (!p.small_tma) { cp_async_wait<0>(); __syncthreads(); }   // phase A reads the y / y1 / Phi_sum rows
     phase_a(0, rot);
+    }
     if (split) pa_arrive();
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
@@ -534,13 +537,12 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         // loads overwrite and whose scale plane (of three) phase A of block blk+1 overwrites.
         // Barrier form (three slots): everybody is done with block blk-1.
         if (split) {
-            mbar_wait(pa_bar, pa_ctr & 1);
-            ++pa_ctr;
+            mbar_wait(pa_bar, (gb + blk) & 1);       // one wait per block since the kernel started
         } else {
             if (!p.small_tma) cp_async_wait<0>();
             __syncthreads();
         }
-        rot = rot + 1 == NW ? 0 : rot + 1;
+        const int rot = (gb + blk + 1) % NW;
         issue(blk + 2, rot);
         wait_block(blk + 1);
         phase_a(blk + 1, rot);
@@ -548,8 +550,8 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
         const unsigned char* buf = smem_raw + ((gb + blk) % NSLOT) * L.buf_bytes;
         const float* sbuf = reinterpret_cast<const float*>(smem_raw + L.part_off + ((gb + blk) % NSBUF) * L.part_bytes);
         const int rho0 = rs + blk * RB;
-        const long long xoff_in = xoff0 + (long long)rho0 * xstride;      // (rho0, px, 4k)
-        const long long xoff_out = xoff_in - R * xstride;                  // (rho0 - R, px, 4k)
+        const int xoff_in = xoff0 + rho0 * xstride;       // (rho0, px, 4k)
+        const int xoff_out = xoff_in - R * xstride;        // (rho0 - R, px, 4k)
         if (rho0 >= fast_lo && rho0 + RB - 1 <= fast_hi) {
 #pragma unroll
             for (int j = 0; j < RB; ++j) {
