@@ -662,6 +662,40 @@ def test_matlab_gapdenoise_loop(sp, golden):
         G.gapdenoise(y, mask, tvm='ITV2D_cham', maxiter=1)
 
 
+def test_data_side_on_device(sp):
+    """measurement synthesis, mask generators and the CASSI stack on the device
+    against the reference's NumPy statements (pnp_sci_test_orig.py:112-136)."""
+    import torch
+    from oracle import pnp_sci as O
+    from scipnp import data as D
+    rng = np.random.default_rng(8)
+    H, W, Cc, F = 20, 26, 4, 3
+    orig = (rng.random((H, W, F * Cc)) * 255).astype(np.float32)
+    mask = (rng.random((H, W, Cc)) * 2).astype(np.float32)              # not normalised: max < 2
+    meas, mk = D.synth_measurements(orig, mask)
+    want = np.zeros((H, W, F), np.float32)
+    for i in range(F):
+        want[:, :, i] = np.sum(orig[:, :, i * Cc:(i + 1) * Cc] * mask, 2)
+    mmax = np.max(mask)
+    np.testing.assert_array_equal(meas.cpu().numpy(), want / mmax)
+    np.testing.assert_array_equal(mk.cpu().numpy(), mask / mmax)
+    noisy, _ = D.synth_measurements(orig, mask, gaussian_noise_level=5, seed=1)
+    again, _ = D.synth_measurements(orig, mask, gaussian_noise_level=5, seed=1)
+    assert torch.equal(noisy, again)
+    d = (noisy - meas) * float(mmax)
+    assert 4.0 < float(d.std()) < 6.0 and abs(float(d.mean())) < 1.0
+    pois, _ = D.synth_measurements(orig, mask, poisson_noise=True, seed=2)
+    assert float((pois * float(mmax) - torch.round(pois * float(mmax))).abs().max()) < 1e-3
+    with pytest.raises(ValueError):
+        D.synth_measurements(orig[:, :, :5], mask)
+    m = D.binary_mask(64, 48, 8, p=0.5, seed=3)
+    assert m.shape == (64, 48, 8) and m.is_cuda and set(np.unique(m.cpu().numpy())) <= {0.0, 1.0}
+    assert 0.45 < float(m.mean()) < 0.55
+    assert torch.equal(m, D.binary_mask(64, 48, 8, p=0.5, seed=3))
+    m2 = (rng.random((12, 9)) > 0.5).astype(np.float32)
+    np.testing.assert_array_equal(D.shift_mask(m2, 5, 2).cpu().numpy(), O.cassi_shift_mask(m2, 5, 2))
+
+
 def test_c_abi_kernel_entries_directly(sp):
     """The stateless C entries called with raw device pointers: one fused iteration equals
     scipnp_gap_project + scipnp_tv_chambolle, and the ADMM pieces compose to the reference update."""
