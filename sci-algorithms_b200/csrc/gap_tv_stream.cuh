@@ -311,10 +311,10 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
     const size_t frame_b = (size_t)b * H * W * C;        // batch offsets
     const size_t meas_b = (size_t)b * H * W;
 
-    // ---- producer: thread 0 programs the TMA unit, RB rows per block ------------------------------
-    //      2*NG*K boxes of x / Phi (+ 3*NG rows of y, y1, Phi_sum) land in slot blk % 3 and
-    //      complete on that slot's mbarrier.  Pixels left/right of the image are zero-filled by
-    //      the TMA unit; rows past the segment are loaded but never used.
+    // ---- producer: one lane (of the warp whose turn it is, see vwarp below) programs the TMA unit,
+    //      RB rows per block: 2*NG*NSUB boxes of x / Phi (+ 3*NG rows of y, y1, Phi_sum) land in slot
+    //      blk % NSLOT and complete on that slot's mbarrier.  Pixels left/right of the image are
+    //      zero-filled by the TMA unit; rows past the segment are loaded but never used.
     constexpr uint32_t kTileTx = (CASSI ? 1u : 2u) * NG * K * BOX_BYTES;   // CASSI: no Phi stack to load
     constexpr uint32_t kSmallTx = (MODE == MODE_GAP_ACC ? 3u : 2u) * NG * RB * 32 * 4;
     const int rowc0 = b * H;                              // row coordinate of the batch element
@@ -589,7 +589,7 @@ gap_tv_stream_kernel(const FusedParams p, const __grid_constant__ FusedMaps maps
                 if (lane == 0 && grp_live) atomicAdd(p.energy + ((size_t)b * C + 4 * k + ch) * R + i, (double)v);
             }
     }
-    // segment boundary: every warp is done with the staging ring and the partial sums
+    // segment boundary: every warp is done with the staging ring and the scale planes
     gb += nblk;
     if (!p.small_tma) cp_async_wait<0>();
     __syncthreads();
