@@ -91,7 +91,11 @@ class HostPipeline:
             self._h = None
             self._keep = {}
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def __enter__(self):
         return self
