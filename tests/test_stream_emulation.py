@@ -130,3 +130,55 @@ def test_work_split_covers_every_row_once_and_is_balanced():
         assert max(loads) <= per_cta + SEG_COST
         full = [l for l in loads if l][:-2]
         assert all(l >= per_cta - 2 * SEG_COST for l in full)
+
+
+# -- the whole outer iteration as the kernel forms it ---------------------------------------------
+
+def _tv_stack(x, weight, T):
+    return np.stack([tv_chambolle_2d(x[:, :, c], weight=weight, eps=0.0, n_iter_max=T)
+                     for c in range(x.shape[2])], axis=2)
+
+
+def test_gap_iteration_as_fused():
+    """Phase A + stage 0 + pipeline: s = (y1_new - yb)/Phi_sum per pixel, f = x + lambda*s*Phi per
+    channel, TV per channel (pnp_sci_algo.py:640-650)."""
+    from oracle import pnp_sci as O
+    rng = np.random.default_rng(2)
+    H, W, C, T, lam = 21, 40, 4, 5, 0.75
+    Phi = (rng.random((H, W, C)) <= 0.5).astype(np.float64)
+    x = rng.random((H, W, C))
+    y = rng.random((H, W)) * C / 2
+    y1 = rng.random((H, W)) * 0.1
+    ps = O.phi_sum(Phi)
+    # reference statements
+    yb = O.A_(x, Phi)
+    y1_ref = y1 + (y - yb)
+    want = _tv_stack(x + lam * O.At_((y1_ref - yb) / ps, Phi), 0.3, T)
+    # kernel form: one scale per pixel from the full dot product, then channel by channel
+    s = ((y1 + (y - (x * Phi).sum(2))) - (x * Phi).sum(2)) / ps
+    got = np.stack([stream_tv(x[:, :, c] + (lam * s) * Phi[:, :, c], 0.3, T, grid=3) for c in range(C)], axis=2)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+
+
+def test_admm_multiplier_comes_out_of_the_f_delay_line():
+    """ADMM (pnp_sci_algo.py:808-836): with f = x - b = theta + lambda*s*Phi the TV input, the
+    multiplier update b - (x - theta_new) is theta_new - f, so the fused kernel needs no copy of b
+    beyond the projection."""
+    from oracle import pnp_sci as O
+    rng = np.random.default_rng(4)
+    H, W, C, T, lam, gamma = 17, 33, 3, 4, 1.0, 0.01
+    Phi = (rng.random((H, W, C)) <= 0.5).astype(np.float64)
+    theta = rng.random((H, W, C))
+    b = 0.1 * rng.standard_normal((H, W, C))
+    y = rng.random((H, W)) * C / 2
+    ps = O.phi_sum(Phi)
+    yb = O.A_(theta + b, Phi)
+    x = (theta + b) + lam * O.At_((y - yb) / (ps + gamma), Phi)
+    theta_ref = _tv_stack(x - b, 0.3, T)
+    b_ref = b - (x - theta_ref)
+    s = (y - ((theta + b) * Phi).sum(2)) / (ps + gamma)
+    f = theta + (lam * s)[:, :, None] * Phi
+    theta_new = np.stack([stream_tv(f[:, :, c], 0.3, T, grid=2) for c in range(C)], axis=2)
+    np.testing.assert_allclose(theta_new, theta_ref, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(theta_new - f, b_ref, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(f + b, x, rtol=0, atol=1e-12)          # the x that admm_denoise returns
