@@ -133,6 +133,12 @@ int scipnp_gap_tv_fused(const float *x_in, float *x_out,
                         void *workspace, size_t workspace_bytes, int *flags_dev,
                         void *stream);
 
+/* Which fused kernel scipnp_gap_tv_fused and the solver use: 0 = automatic (the warp-specialised
+ * kernel csrc/gap_tv_ws.cuh where it applies: GAP, C % 4 == 0, C <= 24, W % 4 == 0; the stream kernel
+ * csrc/gap_tv_stream.cuh otherwise), 1 = stream kernel only, 2 = same as 0.  Process-wide; meant for
+ * tests and profiling (environment: SCIPNP_FUSED_VARIANT).  No reference counterpart.          */
+int scipnp_set_fused_variant(int variant);
+
 /* R8  Bayer sub-lattice (pnp_sci_algo.py:99,116-137,255-257): split a
  *     [H][W][C] mosaic stack into 4 half-resolution stacks [4][H/2][W/2][C]
  *     (order (0,0),(0,1),(1,0),(1,1)) and back.  C = 1 handles [H][W] planes.   */

@@ -76,6 +76,27 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+}  // namespace
+
+// generic tiled float32 tensor map (shared with gap_tv_ws.cu)
+int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box, int l2_promotion_128) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SCIPNP_ECUDA; }
+    cuuint64_t d[5], s[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     l2_promotion_128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rank %d) failed with CUresult %d", rank, (int)r); return SCIPNP_ECUDA; }
+    return SCIPNP_OK;
+}
+
+namespace {
+
 // frame stack [rows][W][C] -> boxes of RB rows x 32 pixels x 4*SUBK channels (fused_subk)
 int make_frame_map(CUtensorMap* tm, const float* base, long long rows, int W, int C) {
     EncodeTiledFn enc = encode_tiled_fn();
@@ -124,7 +145,8 @@ bool fused_cassi_supported(int mode, int B, int H, int W, int C, int tv_iter_max
 size_t fused_workspace_bytes(int B, int H, int W, int C, int tv_iter_max) {
     (void)H; (void)W;
     int R = tv_iter_max > 1 ? tv_iter_max - 1 : 1;
-    return ((size_t)B * C * R * sizeof(double) + 255) & ~(size_t)255;
+    // energy accumulators + 16 bytes for the last-CTA ticket of the warp-specialised kernel
+    return ((size_t)B * C * R * sizeof(double) + 16 + 255) & ~(size_t)255;
 }
 
 int launch_fused(const FusedArgs& a, cudaStream_t st) {
@@ -150,6 +172,7 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
         set_error("fused GAP-TV kernel ping-pongs: in and out buffers must differ");
         return SCIPNP_EINVAL;
     }
+    if (fused_ws_supported(a)) return launch_fused_ws(a, st);
     const int R = a.tv_iter_max - 1;
     FusedParams fp{};
     fp.x_in = a.x_in; fp.x_out = a.x_out; fp.y1_in = a.y1_in; fp.y1_out = a.y1_out;
@@ -196,7 +219,7 @@ int launch_fused(const FusedArgs& a, cudaStream_t st) {
     // the check kernel leaves the accumulators zeroed; a caller that owns the workspace and always
     // passes a flag (the solver) therefore clears it once, everybody else per launch
     if (!(a.workspace_clean && a.flag && R > 1))
-        SCIPNP_CUDA(cudaMemsetAsync(fp.energy, 0, (size_t)a.B * a.C * R * sizeof(double), st));
+        SCIPNP_CUDA(cudaMemsetAsync(fp.energy, 0, fused_workspace_bytes(a.B, a.H, a.W, a.C, a.tv_iter_max), st));
     int rc = SCIPNP_OK;
     if (cassi) rc = launch_stream_cassi_r4(a.mode, fp.K, fp, maps, cp, grid, st);
     else switch (R) {

@@ -1,0 +1,230 @@
+// Host side of the warp-specialised fused GAP-TV kernel (gap_tv_ws.cuh): work split, TMA descriptors
+// (cached per buffer set: x ping-pongs between two buffers, so a solver sees two sets), launch.
+#include "gap_tv_ws.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+namespace scipnp {
+
+using namespace wsk;
+
+int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const unsigned long long* dims,
+                        const unsigned long long* strides_bytes, const unsigned* box, int l2_promotion_128);
+
+namespace {
+
+int g_variant = -1;      // -1: from the environment (SCIPNP_FUSED_VARIANT), 0: auto, 1: stream kernel, 2: ws kernel
+
+struct MapKey {
+    const float *x_in, *x_out, *phi, *y, *y1, *ps;
+    int B, H, W, C, own, phi_batched;
+    bool operator==(const MapKey& o) const {
+        return x_in == o.x_in && x_out == o.x_out && phi == o.phi && y == o.y && y1 == o.y1 && ps == o.ps &&
+               B == o.B && H == o.H && W == o.W && C == o.C && own == o.own && phi_batched == o.phi_batched;
+    }
+};
+struct MapEntry { MapKey key; WsMaps maps; bool valid = false; unsigned long long stamp = 0; };
+constexpr int kMapCache = 16;
+MapEntry g_cache[kMapCache];
+unsigned long long g_stamp = 0;
+std::mutex g_cache_mu;
+
+int build_maps(const MapKey& k, WsMaps* m) {
+    const unsigned long long rows = (unsigned long long)k.B * k.H, prows = k.phi_batched ? rows : (unsigned long long)k.H;
+    {   // frames [rows][W][C]: box = WRB rows x GW pixels x whole pixels
+        unsigned long long dims[3] = {(unsigned long long)k.C, (unsigned long long)k.W, rows};
+        unsigned long long str[2] = {(unsigned long long)k.C * 4, (unsigned long long)k.W * k.C * 4};
+        unsigned box[3] = {(unsigned)k.C, GW, WRB};
+        if (int e = make_tensor_map_f32(&m->x, k.x_in, 3, dims, str, box, 1)) return e;
+        dims[2] = prows;
+        if (int e = make_tensor_map_f32(&m->phi, k.phi, 3, dims, str, box, 1)) return e;
+    }
+    {   // measurement planes [rows][W]
+        unsigned long long dims[2] = {(unsigned long long)k.W, rows};
+        unsigned long long str[1] = {(unsigned long long)k.W * 4};
+        unsigned box[2] = {GW, WRB};
+        if (int e = make_tensor_map_f32(&m->y, k.y, 2, dims, str, box, 0)) return e;
+        if (int e = make_tensor_map_f32(&m->y1, k.y1 ? k.y1 : k.y, 2, dims, str, box, 0)) return e;
+        dims[1] = prows;
+        if (int e = make_tensor_map_f32(&m->ps, k.ps, 2, dims, str, box, 0)) return e;
+    }
+    {   // output frames as [rows][C/4][W][4]: a box is one row x all chunks x the owned pixels of a group,
+        // chunk-major in shared memory
+        unsigned long long dims[4] = {4, (unsigned long long)k.W, (unsigned long long)k.C / 4, rows};
+        unsigned long long str[3] = {(unsigned long long)k.C * 4, 16, (unsigned long long)k.W * k.C * 4};
+        unsigned box[4] = {4, (unsigned)k.own, (unsigned)k.C / 4, 1};
+        if (int e = make_tensor_map_f32(&m->out, k.x_out, 4, dims, str, box, 0)) return e;
+    }
+    return SCIPNP_OK;
+}
+
+int get_maps(const MapKey& k, WsMaps* out) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int victim = 0;
+    for (int i = 0; i < kMapCache; ++i) {
+        if (g_cache[i].valid && g_cache[i].key == k) {
+            g_cache[i].stamp = ++g_stamp;
+            *out = g_cache[i].maps;
+            return SCIPNP_OK;
+        }
+        if (!g_cache[i].valid) victim = i;
+        else if (g_cache[victim].valid && g_cache[i].stamp < g_cache[victim].stamp) victim = i;
+    }
+    MapEntry& e = g_cache[victim];
+    e.valid = false;
+    if (int rc = build_maps(k, &e.maps)) return rc;
+    e.key = k;
+    e.valid = true;
+    e.stamp = ++g_stamp;
+    *out = e.maps;
+    return SCIPNP_OK;
+}
+
+}  // namespace
+
+int fused_variant() {
+    if (g_variant < 0) {
+        const char* e = getenv("SCIPNP_FUSED_VARIANT");
+        g_variant = e ? atoi(e) : 0;
+        if (g_variant < 0 || g_variant > 2) g_variant = 0;
+    }
+    return g_variant;
+}
+
+bool fused_ws_supported(const FusedArgs& a) {
+    if (fused_variant() == 1) return false;
+    if (a.mode != MODE_GAP_ACC && a.mode != MODE_GAP_PLAIN) return false;
+    if (a.mask2d) return false;                                   // CASSI index-offset masks: stream kernel
+    if (a.clip01) return false;
+    const int Q = a.C / 2;
+#ifdef SCIPNP_FUSED_FAST_BUILD
+    if (a.C != 8 && a.C != 24) return false;
+#else
+    if (a.C % 4 != 0 || a.C < 4 || a.C > 24 || Q == 0) return false;
+#endif
+    if (a.tv_iter_max < 3 || a.tv_iter_max > 5) return false;
+    if (a.W % 4 != 0 || a.H < 1 || a.B < 1) return false;         // TMA row pitch of the planes; atomic pixel pairs
+    if ((long long)a.B * a.H >= (1LL << 31)) return false;
+    if (!aligned16(a.x_in) || !aligned16(a.x_out) || !aligned16(a.Phi) || !aligned16(a.y) || !aligned16(a.Phi_sum)) return false;
+    if (a.mode == MODE_GAP_ACC && (!a.y1_in || !a.y1_out || !aligned16(a.y1_in))) return false;
+    return true;
+}
+
+// owned pixels per group and row segments per strip: one CTA per SM, as few waves as possible, long segments
+static void ws_split(int B, int H, int W, int Q, int R, int* own_out, int* nseg_out) {
+    const int NGRP = ws_groups(Q), nsm = num_sms();
+    long long best = -1;
+    int bown = OWN_MAX, bseg = 1;
+    for (int own = OWN_MAX; own >= 32; own -= 4) {
+        const int ngroups = (W + own - 1) / own, nstrips = (ngroups + NGRP - 1) / NGRP;
+        const int maxseg = H / 8 > 1 ? H / 8 : 1;
+        for (int nseg = 1; nseg <= maxseg && nseg <= 4096; ++nseg) {
+            const long long ctas = (long long)B * nstrips * nseg;
+            const long long waves = (ctas + nsm - 1) / nsm;
+            const long long rows = (H + nseg - 1) / nseg + 2 * R + 8;       // steps per CTA incl. warm-up, drain, fill
+            const long long cost = waves * rows;
+            if (best < 0 || cost < best) { best = cost; bown = own; bseg = nseg; }
+            if (waves > 1 && ctas > 8LL * nsm) break;
+        }
+    }
+    *own_out = bown;
+    *nseg_out = bseg;
+}
+
+int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
+    const int R = a.tv_iter_max - 1, Q = a.C / 2;
+    WsParams p{};
+    p.y1_out = a.y1_out;
+    p.energy = reinterpret_cast<double*>(a.workspace);
+    p.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.workspace) + fused_workspace_bytes(a.B, a.H, a.W, a.C, a.tv_iter_max) - 16);
+    p.flag = (a.flag && R > 1) ? a.flag : nullptr;
+    p.tv_eps = a.tv_eps;
+    p.lambda = a.lambda;
+    p.tv_c = (float)(0.25 / a.tv_weight);
+    p.tv_w = (float)a.tv_weight;
+    p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C;
+    p.phi_batched = a.phi_batched ? 1 : 0;
+    int own = OWN_MAX, nseg = 1;
+    ws_split(a.B, a.H, a.W, Q, R, &own, &nseg);
+    if (const char* e = getenv("SCIPNP_WS_OWN")) { int v = atoi(e); if (v >= 4 && v <= OWN_MAX && v % 4 == 0) own = v; }
+    if (const char* e = getenv("SCIPNP_WS_NSEG")) { int v = atoi(e); if (v >= 1 && v <= a.H) nseg = v; }
+    p.own = own;
+    p.nseg = nseg;
+    p.ngroups = (a.W + own - 1) / own;
+    p.nstrips = (p.ngroups + ws_groups(Q) - 1) / ws_groups(Q);
+    const long long ctas = (long long)a.B * p.nstrips * nseg;
+    if (ctas > 0x7fffffffLL) { set_error("scene too large for one launch"); return SCIPNP_EINVAL; }
+    MapKey key{a.x_in, a.x_out, a.Phi, a.y, a.mode == MODE_GAP_ACC ? a.y1_in : nullptr, a.Phi_sum,
+               a.B, a.H, a.W, a.C, own, p.phi_batched};
+    alignas(64) WsMaps maps;
+    if (int e = get_maps(key, &maps)) return e;
+    if (!(a.workspace_clean && a.flag && R > 1))
+        SCIPNP_CUDA(cudaMemsetAsync(a.workspace, 0, fused_workspace_bytes(a.B, a.H, a.W, a.C, a.tv_iter_max), st));
+    // SCIPNP_WS_PROF=1: per-warp cycle counters of CTA 0 and of the last CTA, printed after the launch (profiling only)
+    static const bool prof_on = getenv("SCIPNP_WS_PROF") != nullptr;
+    long long* prof = nullptr;
+    const int nwarp = ws_threads(Q) / 32;
+    if (prof_on) {
+        SCIPNP_CUDA(cudaMalloc(&prof, (size_t)ctas * nwarp * 4 * sizeof(long long)));
+        SCIPNP_CUDA(cudaMemsetAsync(prof, 0, (size_t)ctas * nwarp * 4 * sizeof(long long), st));
+        p.prof = prof;
+    }
+    int rc;
+    switch (R) {
+        case 2: rc = ws_launch_r<2>(a.mode, Q, p, maps, (int)ctas, st); break;
+        case 3: rc = ws_launch_r<3>(a.mode, Q, p, maps, (int)ctas, st); break;
+        case 4: rc = ws_launch_r<4>(a.mode, Q, p, maps, (int)ctas, st); break;
+        default: set_error("unsupported tv_iter_max"); return SCIPNP_EINVAL;
+    }
+    if (rc) return rc;
+    count_launch();
+    if (prof_on) {
+        std::vector<long long> h((size_t)ctas * nwarp * 4);
+        SCIPNP_CUDA(cudaStreamSynchronize(st));
+        SCIPNP_CUDA(cudaMemcpy(h.data(), prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(prof);
+        static int printed = 0;
+        if (printed++ % 8 == 3) {
+            const int ncw = ws_consumers(Q);
+            std::vector<std::pair<long long, long long>> dur;
+            for (long long c = 0; c < ctas; ++c) dur.push_back({h[((size_t)c * nwarp) * 4], c});
+            std::sort(dur.begin(), dur.end());
+            fprintf(stderr, "[ws prof] consumer-0 cycles over %lld CTAs: min %lld (cta %lld)  median %lld  max %lld (cta %lld); slowest:",
+                    ctas, dur.front().first, dur.front().second, dur[dur.size() / 2].first, dur.back().first, dur.back().second);
+            for (size_t i = dur.size() > 6 ? dur.size() - 6 : 0; i < dur.size(); ++i) fprintf(stderr, " %lld:%lld", dur[i].second, dur[i].first);
+            fprintf(stderr, "\n");
+            for (long long cta : {0LL, ctas / 2, ctas - 1}) {
+                fprintf(stderr, "[ws prof] cta %lld own=%d nseg=%d grid=%lld\n", cta, own, nseg, ctas);
+                for (int w = 0; w < nwarp; ++w) {
+                    const long long* r = &h[((size_t)cta * nwarp + w) * 4];
+                    if (w < ncw) fprintf(stderr, "  consumer %2d: total %9lld  wait f_full %9lld  wait out_empty %9lld\n", w, r[0], r[1], r[2]);
+                    else fprintf(stderr, "  producer %2d: total %9lld  wait raw %9lld  wait f_empty(+stores) %9lld  bar %9lld\n", w, r[0], r[1], r[2], r[3]);
+                }
+            }
+        }
+    }
+    return check_launch("gap_tv_ws_kernel");
+}
+
+// buffers that were freed must not be found in the descriptor cache by a later allocation at the same address
+// with different contents of the descriptor (same key => same descriptor, so this is only hygiene)
+void fused_ws_forget(const void* base) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto& e : g_cache)
+        if (e.valid && (e.key.x_in == base || e.key.x_out == base || e.key.phi == base)) e.valid = false;
+}
+
+}  // namespace scipnp
+
+extern "C" {
+
+// 0: automatic (warp-specialised kernel where it applies), 1: stream kernel only, 2: same as 0
+int scipnp_set_fused_variant(int v) {
+    if (v < 0 || v > 2) { scipnp::set_error("fused variant must be 0, 1 or 2"); return SCIPNP_EINVAL; }
+    scipnp::g_variant = v;
+    return SCIPNP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,612 @@
+// Warp-specialised one-pass GAP-TV iteration (second-generation fused kernel, sm_100a).
+//
+// Same mathematics and the same HBM traffic as gap_tv_stream.cuh (one launch = one outer iteration
+// of pnp_sci_algo.py:640-650 with denoiser='tv'), different mapping onto the SM:
+//
+//   * The CTA is split by role.  PRODUCER warps turn TMA-staged rows of x / Phi / y / y1 / Phi_sum
+//     into the TV input f = x + lambda*s*Phi (one thread per (row, pixel): the whole dot product over
+//     the C channels, the y1 update, the scale, f for every channel) and leave f in shared memory in a
+//     channel-pair-major layout.  CONSUMER warps run the Chambolle pipeline on f and never touch the
+//     projection.  One STORER lane hands finished rows to the TMA unit.  The roles are coupled only
+//     through mbarrier rings (raw tiles, f tiles, output tiles), so no warp waits for a CTA-wide barrier.
+//   * A consumer lane owns two horizontally adjacent pixels x one channel pair (4 values, two packed
+//     float2 chains): a warp covers 64 pixels of one channel pair.  Half of the horizontal neighbours
+//     are in the thread's own registers (4 SHFL per dual iteration instead of 8), and the halo of a
+//     group is 4 pixels = 2 lanes per side, i.e. up to 56 of 64 pixels are owned (24 of 32 before).
+//   * Output rows are assembled in a chunk-major shared-memory tile ([C/4][own][4]) and written with TMA
+//     tensor stores of exactly the owned pixels; y1 is written by the producers (coalesced).
+//   * One CTA per SM, one row segment per CTA: grid = batch x column strips x row segments, strips and
+//     segments chosen on the host so that the grid is one full wave and neighbouring strips walk down
+//     the image in lockstep (the halo columns they share then come out of L2, not DRAM).
+//
+// Dual-iteration pipeline of a consumer (row streaming, one-row lag per dual iteration), per step t:
+//   stage i (0..R-1) receives out_i(t-i), advances the dual variable of row u = t-i-1 and emits
+//   out_{i+1}(u); out_R(t-R) leaves the pipeline.  State per stage: out_i(u), p^{i+1}(u-1) (both
+//   components: the vertical one closes the divergence of this stage, both feed stage i+1), the
+//   horizontal difference of the pair's right pixel, and the f delay line.
+#pragma once
+#include "gap_tv_stream.cuh"
+
+namespace scipnp {
+namespace wsk {
+
+using namespace fusedk;     // PTX helpers, P2 arithmetic
+
+constexpr int WRB = 4;            // rows per staged block
+constexpr int GW = 64;            // pixels per group tile (lane = 2 pixels)
+constexpr int HALO = 4;           // halo pixels per side of a group (2 lanes)
+constexpr int OWN_MAX = GW - 2 * HALO;
+constexpr int NPROD = 4;          // producer warps
+constexpr int NRAW = 2;           // ring depth of the raw (TMA-staged) tiles
+constexpr int NOUT = 2;           // ring depth of the output tiles
+
+struct WsParams {
+    float* y1_out;                // accelerated GAP: y1 written by the producers
+    double* energy;               // [B][C][R] partial sums of d^2 + w*|g|
+    int* flag;                    // early-stop flag (may be null: no check)
+    unsigned* ticket;             // last-CTA detection for the in-kernel energy check
+    double tv_eps;
+    float lambda, tv_c, tv_w;     // tv_c = tau / weight
+    int B, H, W, C;
+    int own;                      // owned pixels per group (multiple of 4, <= OWN_MAX)
+    int ngroups;                  // ceil(W / own)
+    int nstrips;                  // ceil(ngroups / NGRP): column strips (CTAs across the image)
+    int nseg;                     // row segments per strip
+    int phi_batched;
+    long long* prof;              // optional [grid][warps][4] cycle counters (SCIPNP_WS_PROF), else null
+};
+
+struct WsMaps { CUtensorMap x, phi, y, y1, ps, out; };
+
+// pixel groups per CTA for Q = C/2 channel pairs: about 12 consumer warps
+__host__ __device__ constexpr int ws_groups(int Q) { return 12 / Q < 1 ? 1 : 12 / Q; }
+__host__ __device__ constexpr int ws_consumers(int Q) { return ws_groups(Q) * Q; }
+__host__ __device__ constexpr int ws_threads(int Q) { return (ws_consumers(Q) + NPROD) * 32; }
+
+struct WsSmem {
+    int x_bytes;        // x tiles of one raw slot: [NGRP][WRB][GW][C]
+    int small_off;      // y / y1 / Phi_sum rows inside a raw slot: [3][NGRP][WRB][GW]
+    int raw_bytes;      // one raw slot
+    int f_off, f_bytes, nf;
+    int out_off, out_sub, out_bytes;   // out_sub: bytes of one (row, group) sub-tile (128-byte multiple)
+    int bar_off;
+    int total;
+};
+__host__ __device__ constexpr WsSmem ws_smem(int Q) {
+    WsSmem s{};
+    const int NGRP = ws_groups(Q), C = 2 * Q;
+    s.x_bytes = NGRP * WRB * GW * C * 4;
+    s.small_off = 2 * s.x_bytes;
+    s.raw_bytes = s.small_off + 3 * NGRP * WRB * GW * 4;
+    s.f_off = NRAW * s.raw_bytes;
+    s.f_bytes = WRB * NGRP * Q * GW * 2 * 4;
+    s.out_sub = (Q / 2) * OWN_MAX * 16;
+    s.out_bytes = WRB * NGRP * s.out_sub;
+    const int fixed = s.f_off + NOUT * s.out_bytes + 256;
+    s.nf = (fixed + 3 * s.f_bytes <= 232448 - 1024) ? 3 : 2;
+    s.out_off = s.f_off + s.nf * s.f_bytes;
+    s.bar_off = s.out_off + NOUT * s.out_bytes;
+    s.total = s.bar_off + 256;
+    return s;
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(NPROD * 32) : "memory"); }
+
+// non-blocking poll (test_wait returns at once; try_wait may suspend the thread for a system-dependent time)
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ P2 shfl_dn2(P2 a) {
+    return make_float2(__shfl_down_sync(0xffffffffu, a.x, 1), __shfl_down_sync(0xffffffffu, a.y, 1));
+}
+
+// Register state of a consumer lane: [.][0] = left pixel (A), [.][1] = right pixel (B); a P2 holds the two
+// channels of the pair.
+template <int R>
+struct WsPipe {
+    P2 o_prev[R][2];     // out_i(u)
+    P2 g1b[R];           // horizontal difference of out_i(u) at the right pixel (its neighbour is a SHFL)
+    P2 P0[R][2];         // p^{i+1}(u-1), vertical component
+    P2 P1[R][2];         //               horizontal component
+    P2 fd[R][2];         // fd[j] = f(t-1-j)
+    P2 en[R];            // energy partials of dual iterations 0..R-1 (both pixels)
+};
+
+struct WsConst {
+    P2 mone2, mtau2, tvc2, one2, w2;
+    float tvw, pair_in, right_in;    // pair inside the image; pixel right of B inside the image
+    int rs, r0, r1, H;
+};
+
+// One pipeline step: f_new = f(t) enters, out_R(t-R) is returned in o_out.
+// PATH 1 (fast): every row touched lies inside [r0, r1) and the image and the whole group lies inside the image.
+// PATH 2 (edge): the rows as in 1, but the group hangs over the left or right image edge: pixel masks only.
+// PATH 0 (general): row masks and pixel masks.
+template <int R, int PATH>
+__device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, const P2 (&f_new)[2], P2 (&o_out)[2]) {
+    constexpr bool FAST = PATH != 0;          // no row masks
+    constexpr bool PXM = PATH != 1;           // pixel masks
+    P2 o_new[2] = {f_new[0], f_new[1]};
+#ifdef WS_EXP
+    P2 o_last[2] = {f_new[0], f_new[1]};
+#endif
+    P2 pi0[2], pi1[2];
+    const P2 z = splat(0.f);
+    pi0[0] = z; pi0[1] = z; pi1[0] = z; pi1[1] = z;              // p^0 = 0
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int row_new = t - i, u = row_new - 1;
+        P2 m2, md2, me2, wm2;
+        if (FAST && PXM) m2 = splat(c.pair_in);
+        if (!FAST) {
+            m2 = splat(((u >= c.rs) && (u < c.H)) ? c.pair_in : 0.f);
+            md2 = splat(row_new < c.H ? 1.f : 0.f);
+            const float me = (u >= c.r0 && u < c.r1) ? 1.f : 0.f;
+            me2 = splat(me);
+            wm2 = splat(me * c.tvw);
+        } else {
+            wm2 = c.w2;
+        }
+#ifdef WS_EXP
+        if (FAST && (WS_EXP == 1 || (WS_EXP == 2 && i == R / 2))) { o_new[0] = f_new[0]; o_new[1] = f_new[1]; }
+#endif
+        // right neighbour of B in the new row: the next lane's A
+        const P2 o_rb = shfl_dn2(o_new[0]);
+        P2 g1[2], g0[2];
+        g1[0] = fma2(S.o_prev[i][0], c.mone2, S.o_prev[i][1]);     // out_i(u, B) - out_i(u, A)
+        g1[1] = S.g1b[i];
+        P2 pn0[2], pn1[2], nrm[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            g0[q] = fma2(S.o_prev[i][q], c.mone2, o_new[q]);
+            if (!FAST) g0[q] = mul2(g0[q], md2);
+            nrm[q] = sqrt2(fma2(g0[q], g0[q], mul2(g1[q], g1[q])));
+            P2 r = rcp2(fma2(nrm[q], c.tvc2, c.one2));
+            if (PXM) r = mul2(r, m2);
+            pn0[q] = mul2(fma2(g0[q], c.mtau2, pi0[q]), r);
+            pn1[q] = mul2(fma2(g1[q], c.mtau2, pi1[q]), r);
+        }
+        // D(p^{i+1})(u) = (p0(u-1) - p0(u)) + (p1(u, left) - p1(u)); the left neighbour of A is the previous lane's B
+        const P2 p1l_a = shfl_up2(pn1[1]);
+        P2 d[2];
+        d[0] = add2(fma2(pn0[0], c.mone2, S.P0[i][0]), fma2(pn1[0], c.mone2, p1l_a));
+        d[1] = add2(fma2(pn0[1], c.mone2, S.P0[i][1]), fma2(pn1[1], c.mone2, pn1[0]));
+        // energies: w*|grad out_i|(u) belongs to iteration i, D(p^{i+1})(u)^2 to iteration i+1
+#if defined(WS_EXP) && WS_EXP == 4
+        if (!FAST)
+#endif
+        {
+        S.en[i] = fma2(nrm[0], wm2, S.en[i]);
+        S.en[i] = fma2(nrm[1], wm2, S.en[i]);
+        }
+#if defined(WS_EXP) && WS_EXP == 4
+        if (!FAST)
+#endif
+        if (i + 1 < R) {
+            if (FAST) {
+                S.en[i + 1] = fma2(d[0], d[0], S.en[i + 1]);
+                S.en[i + 1] = fma2(d[1], d[1], S.en[i + 1]);
+            } else {
+                S.en[i + 1] = fma2(mul2(d[0], me2), d[0], S.en[i + 1]);
+                S.en[i + 1] = fma2(mul2(d[1], me2), d[1], S.en[i + 1]);
+            }
+        }
+        // state of this stage for the next step
+        P2 g1b_new = fma2(o_new[1], c.mone2, o_rb);
+        if (PXM) g1b_new = mul2(g1b_new, splat(c.right_in));
+        S.g1b[i] = g1b_new;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const P2 o_next = add2(S.fd[i][q], d[q]);
+            // the dual variable stage i+1 needs now is the one this stage produced in the previous step
+            pi0[q] = S.P0[i][q];
+            pi1[q] = S.P1[i][q];
+            S.P0[i][q] = pn0[q];
+            S.P1[i][q] = pn1[q];
+            S.o_prev[i][q] = o_new[q];
+            o_new[q] = o_next;
+#ifdef WS_EXP
+            o_last[q] = add2(o_last[q], o_next);
+#endif
+        }
+    }
+#ifdef WS_EXP
+    if (FAST && (WS_EXP == 1 || WS_EXP == 2)) { o_new[0] = o_last[0]; o_new[1] = o_last[1]; }
+#endif
+#pragma unroll
+    for (int i = R - 1; i > 0; --i) { S.fd[i][0] = S.fd[i - 1][0]; S.fd[i][1] = S.fd[i - 1][1]; }
+    S.fd[0][0] = f_new[0];
+    S.fd[0][1] = f_new[1];
+    o_out[0] = o_new[0];
+    o_out[1] = o_new[1];
+}
+
+// MODE: MODE_GAP_ACC or MODE_GAP_PLAIN.  Q = C/2 channel pairs.
+template <int R, int MODE, int Q>
+__global__ void __launch_bounds__(ws_threads(Q), 1)
+gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
+    constexpr int NGRP = ws_groups(Q);
+    constexpr int CW = ws_consumers(Q);
+    constexpr int C = 2 * Q, K = Q / 2;
+    constexpr WsSmem L = ws_smem(Q);
+    constexpr int NF = L.nf;
+    static_assert(Q % 2 == 0, "C must be a multiple of 4");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    // mbarriers: raw_full[NRAW], f_full[NF], f_empty[NF], out_full[NOUT], out_empty[NOUT]
+    const uint32_t bar_raw = smem_base + L.bar_off;
+    const uint32_t bar_ffull = bar_raw + 8 * NRAW;
+    const uint32_t bar_fempty = bar_ffull + 8 * NF;
+    const uint32_t bar_ofull = bar_fempty + 8 * NF;
+    const uint32_t bar_oempty = bar_ofull + 8 * NOUT;
+    if (tid == 0) {
+        for (int i = 0; i < NRAW; ++i) mbar_init(bar_raw + 8 * i, 1);
+        for (int i = 0; i < NF; ++i) { mbar_init(bar_ffull + 8 * i, NPROD); mbar_init(bar_fempty + 8 * i, CW); }
+        for (int i = 0; i < NOUT; ++i) { mbar_init(bar_ofull + 8 * i, CW); mbar_init(bar_oempty + 8 * i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        fence_async_smem();
+    }
+    __syncthreads();
+
+    // ---- this CTA's work: one row segment of one column strip of one batch element
+    const int H = p.H, W = p.W, own = p.own;
+    int bid = blockIdx.x;
+    const int seg = bid % p.nseg; bid /= p.nseg;
+    const int strip = bid % p.nstrips;
+    const int b = bid / p.nstrips;
+    const int r0 = (int)((long long)H * seg / p.nseg), r1 = (int)((long long)H * (seg + 1) / p.nseg);
+    const int rs = max(0, r0 - R), t_end = r1 + R;                 // steps t in [rs, t_end)
+    const int nblk = (t_end - rs + WRB - 1) / WRB;
+    const int group0 = strip * NGRP;
+    const int rowc0 = b * H;                                        // row coordinate of the batch element
+    const int phirow0 = p.phi_batched ? b * H : 0;
+
+    if (warp < CW) {
+        // =================================== consumers ===================================
+        const int gi = warp / Q, q = warp - gi * Q;
+        const int grp = group0 + gi;
+        const bool grp_live = grp < p.ngroups;
+        const int base = grp * own - HALO;                          // pixel of lane 0's A
+        const int pxa = base + 2 * lane;
+        const bool pair_in = grp_live && pxa >= 0 && pxa < W;       // W is even and base is even: pairs are atomic
+        const bool own_lane = pair_in && lane >= HALO / 2 && lane < HALO / 2 + own / 2;
+        const bool interior = grp_live && base >= 0 && base + GW <= W;
+        WsPipe<R> S;
+        const P2 z = splat(0.f);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            S.g1b[i] = z; S.en[i] = z;
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) { S.o_prev[i][k2] = z; S.P0[i][k2] = z; S.P1[i][k2] = z; S.fd[i][k2] = z; }
+        }
+        WsConst sc;
+        sc.mone2 = splat(-1.f); sc.mtau2 = splat(-0.25f); sc.tvc2 = splat(p.tv_c); sc.one2 = splat(1.f);
+        sc.w2 = splat(p.tv_w); sc.tvw = p.tv_w;
+        sc.pair_in = pair_in ? 1.f : 0.f;
+        sc.right_in = (pair_in && pxa + 2 < W) ? 1.f : 0.f;
+        sc.rs = rs; sc.r0 = r0; sc.r1 = r1; sc.H = H;
+        // f tile: [WRB][NGRP][Q][GW][2] floats; this lane reads 16 bytes (A.c0 A.c1 B.c0 B.c1)
+        const uint32_t f_lane = smem_base + L.f_off + ((gi * Q + q) * GW + 2 * lane) * 8;
+        constexpr int F_ROW = NGRP * Q * GW * 8;
+        // out tile: [WRB][NGRP] sub-tiles of [K][own][4] floats; chunk k = q/2, half h = q%2
+        const int kq = q >> 1, hq = q & 1;
+        const uint32_t o_lane = smem_base + L.out_off + gi * L.out_sub + ((kq * own + 2 * (lane - HALO / 2)) * 4 + 2 * hq) * 4;
+        constexpr int O_ROW = NGRP * L.out_sub;
+        const int fast_lo = r0 + R, fast_hi = min(r1, H) - 1;
+        long long pw0 = 0, pw1 = 0;
+        const long long pstart = p.prof ? clock64() : 0;
+#pragma unroll 1
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int fs = blk % NF, os = blk % NOUT;
+            long long c0 = 0, c1 = 0;
+            if (p.prof) c0 = clock64();
+            mbar_wait(bar_ffull + 8 * fs, (blk / NF) & 1);
+            if (p.prof) { c1 = clock64(); pw0 += c1 - c0; }
+            mbar_wait(bar_oempty + 8 * os, ((blk / NOUT) & 1) ^ 1);
+            if (p.prof) pw1 += clock64() - c1;
+            const uint32_t fsrc = f_lane + fs * L.f_bytes;
+            const uint32_t odst = o_lane + os * L.out_bytes;
+            const int t0 = rs + blk * WRB;
+            const bool rows_fast = t0 >= fast_lo && t0 + WRB - 1 <= fast_hi;
+            auto fast_block = [&](auto path) {
+                constexpr int PATH = decltype(path)::value;
+#pragma unroll
+                for (int j = 0; j < WRB; ++j) {
+                    float4 fv;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(fv.x), "=f"(fv.y), "=f"(fv.z), "=f"(fv.w) : "r"(fsrc + j * F_ROW));
+                    const P2 f_new[2] = {make_float2(fv.x, fv.y), make_float2(fv.z, fv.w)};
+                    P2 o[2];
+                    ws_step<R, PATH>(S, sc, t0 + j, f_new, o);
+#if defined(WS_EXP) && WS_EXP == 3
+                    if (own_lane && o[0].x == 123.456f) {
+#else
+                    if (own_lane) {
+#endif
+                        asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW), "f"(o[0].x), "f"(o[0].y) : "memory");
+                        asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW + 16), "f"(o[1].x), "f"(o[1].y) : "memory");
+                    }
+                }
+            };
+            if (rows_fast && interior) {
+                fast_block(std::integral_constant<int, 1>{});
+            } else if (rows_fast) {
+                fast_block(std::integral_constant<int, 2>{});
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < WRB; ++j) {
+                    const int t = t0 + j;
+                    if (t < t_end) {
+                        float4 fv;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(fv.x), "=f"(fv.y), "=f"(fv.z), "=f"(fv.w) : "r"(fsrc + j * F_ROW));
+                        const P2 f_new[2] = {make_float2(fv.x, fv.y), make_float2(fv.z, fv.w)};
+                        P2 o[2];
+                        ws_step<R, 0>(S, sc, t, f_new, o);
+                        if (own_lane) {
+                            asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW), "f"(o[0].x), "f"(o[0].y) : "memory");
+                            asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW + 16), "f"(o[1].x), "f"(o[1].y) : "memory");
+                        }
+                    }
+                }
+            }
+            fence_async_smem();                  // the TMA store reads what this warp just wrote
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_ofull + 8 * os);
+                mbar_arrive(bar_fempty + 8 * fs);
+            }
+        }
+        if (p.prof && lane == 0) {
+            long long* pr = p.prof + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * 4;
+            pr[0] = clock64() - pstart; pr[1] = pw0; pr[2] = pw1; pr[3] = 0;
+        }
+        // energy partials: owned lanes only, one atomic per (channel, iteration)
+        if (p.flag != nullptr) {
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    float v = own_lane ? (ch ? S.en[i].y : S.en[i].x) : 0.f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && grp_live) atomicAdd(p.energy + ((size_t)b * C + 2 * q + ch) * R + i, (double)v);
+                }
+        }
+    } else {
+        // =================================== producers ===================================
+        const int ptid = tid - CW * 32;                          // 0 .. NPROD*32-1
+        constexpr int NPT = NPROD * 32;
+        constexpr int NITEM = WRB * NGRP * GW;                   // (row, group, pixel) items per block
+        constexpr uint32_t kTx = 2u * L.x_bytes + (MODE == MODE_GAP_ACC ? 3u : 2u) * NGRP * WRB * GW * 4;
+        auto issue = [&](int blk) {
+            if (blk < nblk && ptid == 0) {
+                const int slot = blk % NRAW;
+                const uint32_t dst = smem_base + slot * L.raw_bytes;
+                const uint32_t bar = bar_raw + 8 * slot;
+                const int row0 = rs + blk * WRB;
+                mbar_expect_tx(bar, kTx);
+#pragma unroll
+                for (int g = 0; g < NGRP; ++g) {
+                    const int px0 = (group0 + g) * own - HALO;
+                    tma_load_3d(dst + g * (WRB * GW * C * 4), &maps.x, 0, px0, rowc0 + row0, bar);
+                    tma_load_3d(dst + L.x_bytes + g * (WRB * GW * C * 4), &maps.phi, 0, px0, phirow0 + row0, bar);
+                    const uint32_t ds = dst + L.small_off + g * (WRB * GW * 4);
+                    tma_load_2d(ds, &maps.y, px0, rowc0 + row0, bar);
+                    if (MODE == MODE_GAP_ACC) tma_load_2d(ds + NGRP * WRB * GW * 4, &maps.y1, px0, rowc0 + row0, bar);
+                    tma_load_2d(ds + 2 * NGRP * WRB * GW * 4, &maps.ps, px0, phirow0 + row0, bar);
+                }
+            }
+        };
+        // The first producer warp is also the storer: whenever every consumer warp has finished the rows of an
+        // output block, its lane 0 hands the owned pixels of the rows inside [r0, r1) to the TMA unit.  It polls
+        // while it waits for the consumers (never blocks on the output ring), so the rings cannot deadlock.
+        const bool storer = warp == CW;
+        int sblk = 0;                                             // next output block to store
+        auto store_block = [&]() {                                // lane 0 of the storer warp
+            const int os = sblk % NOUT;
+            const uint32_t src = smem_base + L.out_off + os * L.out_bytes;
+            for (int j = 0; j < WRB; ++j) {
+                const int orow = rs + sblk * WRB + j - R;
+                if (orow >= r0 && orow < r1) {
+                    for (int g = 0; g < NGRP; ++g)
+                        if (group0 + g < p.ngroups)
+                            tma_store_4d(&maps.out, src + (j * NGRP + g) * L.out_sub, 0, (group0 + g) * own, 0, rowc0 + orow);
+                }
+            }
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(bar_oempty + 8 * os);
+        };
+        auto store_poll = [&]() {
+            if (sblk < nblk) {
+                int ready = 0;
+                if (lane == 0) ready = mbar_try(bar_ofull + 8 * (sblk % NOUT), (sblk / NOUT) & 1) ? 1 : 0;
+                ready = __shfl_sync(0xffffffffu, ready, 0);
+                if (ready) {
+                    if (lane == 0) store_block();
+                    __syncwarp();
+                    ++sblk;
+                }
+            }
+        };
+        long long pw0 = 0, pw1 = 0, pw2 = 0;
+        const long long pstart = p.prof ? clock64() : 0;
+        issue(0);
+        issue(1);
+        const float lam = p.lambda;
+        float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + (size_t)b * H * W : nullptr;
+        // bank pattern of the lane-per-pixel 16-byte reads: pixels are C*4 bytes apart.  For K = 2, 6 every
+        // other group of four lanes visits the chunk pairs in swapped order, for K = 4 the chunk index is
+        // xor-ed with (pixel / 2) % 4; odd K is conflict-free as it is.
+        const int lsw = (K % 4 == 2) ? ((lane >> 2) & 1) : (K % 8 == 4) ? ((lane >> 1) & 3) : 0;
+#pragma unroll 1
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int slot = blk % NRAW, fs = blk % NF;
+            long long c0 = 0, c1 = 0;
+            if (p.prof) c0 = clock64();
+            mbar_wait(bar_raw + 8 * slot, (blk / NRAW) & 1);
+            if (p.prof) { c1 = clock64(); pw0 += c1 - c0; }
+            if (storer) {
+                store_poll();
+                for (;;) {
+                    int ok = 0;
+                    if (lane == 0) ok = mbar_try(bar_fempty + 8 * fs, ((blk / NF) & 1) ^ 1) ? 1 : 0;
+                    if (__shfl_sync(0xffffffffu, ok, 0)) break;
+                    store_poll();
+                    __nanosleep(32);
+                }
+            } else {
+                mbar_wait(bar_fempty + 8 * fs, ((blk / NF) & 1) ^ 1);
+            }
+            if (p.prof) pw1 += clock64() - c1;
+            const unsigned char* raw = smem_raw + slot * L.raw_bytes;
+            unsigned char* fdst = smem_raw + L.f_off + fs * L.f_bytes;
+#pragma unroll 1
+            for (int it = ptid; it < NITEM; it += NPT) {
+                const int px = it & (GW - 1), g = (it / GW) % NGRP, j = it / (GW * NGRP);
+                const int row = rs + blk * WRB + j;
+                const int gpx = (group0 + g) * own - HALO + px;
+                const bool in = (group0 + g) < p.ngroups && gpx >= 0 && gpx < W && row < H;
+                const float4* tx = reinterpret_cast<const float4*>(raw) + ((g * WRB + j) * GW + px) * K;
+                const float4* tp = tx + L.x_bytes / 16;
+                float4 xv[K], pv[K];
+#pragma unroll
+                for (int k0 = 0; k0 < K; ++k0) { xv[k0] = tx[k0 ^ lsw]; pv[k0] = tp[k0 ^ lsw]; }
+                P2 acc2 = splat(0.f);
+#pragma unroll
+                for (int k0 = 0; k0 < K; ++k0) {
+                    acc2 = fma2(make_float2(xv[k0].x, xv[k0].y), make_float2(pv[k0].x, pv[k0].y), acc2);
+                    acc2 = fma2(make_float2(xv[k0].z, xv[k0].w), make_float2(pv[k0].z, pv[k0].w), acc2);
+                }
+                const float acc = acc2.x + acc2.y;
+                const float* sm = reinterpret_cast<const float*>(raw + L.small_off) + (g * WRB + j) * GW + px;
+                const float yv = sm[0];
+                const float psv = sm[2 * NGRP * WRB * GW];
+                float sv;
+                if (MODE == MODE_GAP_ACC) {
+                    const float y1n = sm[NGRP * WRB * GW] + (yv - acc);
+                    if (in && px >= HALO && px < HALO + own && row >= r0 && row < r1) y1o[(size_t)row * W + gpx] = y1n;
+                    sv = (y1n - acc) * fast_rcp(psv);
+                } else {
+                    sv = (yv - acc) * fast_rcp(psv);
+                }
+                const P2 s2 = splat(in ? sv * lam : 0.f);
+                // f tile: [WRB][NGRP][Q][GW][2]
+                float2* frow = reinterpret_cast<float2*>(fdst) + ((j * NGRP + g) * Q) * GW + px;
+#pragma unroll
+                for (int k0 = 0; k0 < K; ++k0) {
+                    const int kc = k0 ^ lsw;
+                    frow[(2 * kc) * GW] = fma2(s2, make_float2(pv[k0].x, pv[k0].y), make_float2(xv[k0].x, xv[k0].y));
+                    frow[(2 * kc + 1) * GW] = fma2(s2, make_float2(pv[k0].z, pv[k0].w), make_float2(xv[k0].z, xv[k0].w));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ffull + 8 * fs);
+            if (p.prof) c0 = clock64();
+            prod_bar();                              // every producer is done reading the raw slot
+            if (p.prof) pw2 += clock64() - c0;
+            issue(blk + NRAW);
+        }
+        if (p.prof && lane == 0) {
+            long long* pr = p.prof + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * 4;
+            pr[0] = clock64() - pstart; pr[1] = pw0; pr[2] = pw1; pr[3] = pw2;
+        }
+        if (storer) {
+            while (sblk < nblk) {
+                mbar_wait(bar_ofull + 8 * (sblk % NOUT), (sblk / NOUT) & 1);
+                if (lane == 0) store_block();
+                __syncwarp();
+                ++sblk;
+            }
+            if (lane == 0) bulk_wait0();
+        }
+    }
+
+    // ---- skimage's stopping rule, replayed by the last CTA on the accumulated energies
+    if (p.flag != nullptr) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const int nslice = p.B * C;
+            bool fired = false;
+            for (int s = tid; s < nslice; s += blockDim.x) {
+                volatile double* e = p.energy + (size_t)s * R;
+                double ev[R];
+#pragma unroll
+                for (int i = 0; i < R; ++i) { ev[i] = e[i]; e[i] = 0.0; }     // leave the accumulators clean
+                double e_prev = ev[0];
+#pragma unroll
+                for (int i = 1; i < R; ++i) {                                   // a stop at i = R changes nothing
+                    if (fabs(e_prev - ev[i]) < p.tv_eps * ev[0]) fired = true;
+                    e_prev = ev[i];
+                }
+            }
+            if (fired) atomicOr(p.flag, 1);
+            if (tid == 0) *p.ticket = 0u;
+        }
+    }
+}
+
+// one launcher per R, defined in ws_inst_r{2,3,4}.cu
+template <int R> int ws_launch_r(int mode, int Q, const WsParams& p, const WsMaps& maps, int grid, cudaStream_t st);
+
+template <int R, int MODE, int Q>
+int ws_launch_q(const WsParams& p, const WsMaps& maps, int grid, cudaStream_t st) {
+    auto kfn = gap_tv_ws_kernel<R, MODE, Q>;
+    constexpr WsSmem L = ws_smem(Q);
+    static bool configured = false;
+    if (!configured) {
+        SCIPNP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        configured = true;
+    }
+    kfn<<<grid, ws_threads(Q), L.total, st>>>(p, maps);
+    return SCIPNP_OK;
+}
+
+template <int R, int MODE>
+int ws_launch_mode(int Q, const WsParams& p, const WsMaps& maps, int grid, cudaStream_t st) {
+    switch (Q) {
+        case 4: return ws_launch_q<R, MODE, 4>(p, maps, grid, st);
+        case 12: return ws_launch_q<R, MODE, 12>(p, maps, grid, st);
+#ifndef SCIPNP_FUSED_FAST_BUILD
+        case 2: return ws_launch_q<R, MODE, 2>(p, maps, grid, st);
+        case 6: return ws_launch_q<R, MODE, 6>(p, maps, grid, st);
+        case 8: return ws_launch_q<R, MODE, 8>(p, maps, grid, st);
+        case 10: return ws_launch_q<R, MODE, 10>(p, maps, grid, st);
+#endif
+    }
+    set_error("warp-specialised fused kernel not built for C = %d", 2 * Q);
+    return SCIPNP_EINVAL;
+}
+
+#define SCIPNP_INSTANTIATE_WS_R(RR)                                                                              \
+    template <> int ws_launch_r<RR>(int mode, int Q, const WsParams& p, const WsMaps& maps, int grid, cudaStream_t st) { \
+        if (mode == MODE_GAP_ACC) return ws_launch_mode<RR, MODE_GAP_ACC>(Q, p, maps, grid, st);                 \
+        return ws_launch_mode<RR, MODE_GAP_PLAIN>(Q, p, maps, grid, st);                                         \
+    }
+
+}  // namespace wsk
+}  // namespace scipnp

@@ -45,5 +45,9 @@ bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
 bool fused_cassi_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
 size_t fused_workspace_bytes(int B, int H, int W, int C, int tv_iter_max);
 int launch_fused(const FusedArgs& a, cudaStream_t st);
+// gap_tv_ws.cu: warp-specialised second-generation kernel (GAP modes, C <= 24, W % 4 == 0)
+bool fused_ws_supported(const FusedArgs& a);
+int launch_fused_ws(const FusedArgs& a, cudaStream_t st);
+int fused_variant();
 
 }  // namespace scipnp

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscipnp.so")
+LIB_PATH = os.environ.get("SCIPNP_LIB") or os.path.join(_HERE, "libscipnp.so")   # SCIPNP_LIB: experiment builds
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "scipnp.h"))
 
 
@@ -64,6 +64,7 @@ _SIGS = {
     "scipnp_gap_tv_fused": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_float, _i,
                                       C.c_double, C.c_double, _i, _i, _i, _i, _i, _i,
                                       _vp, C.c_size_t, _vp, _vp]),
+    "scipnp_set_fused_variant": (C.c_int, [_i]),
     "scipnp_bayer_split": (C.c_int, [_fp, _fp, _i, _i, _i, _vp]),
     "scipnp_bayer_merge": (C.c_int, [_fp, _fp, _i, _i, _i, _vp]),
     "scipnp_cassi_shift_mask": (C.c_int, [_fp, _fp, _i, _i, _i, _i, _vp]),
