@@ -6,7 +6,7 @@
 namespace scipnp {
 
 static thread_local char g_err[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -52,6 +52,6 @@ int scipnp_device_count(void) {
     return n;
 }
 
-long long scipnp_launch_count(void) { return scipnp::g_launches; }
+long long scipnp_launch_count(void) { return scipnp::g_launches.load(); }
 
 }  // extern "C"

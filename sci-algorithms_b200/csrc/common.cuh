@@ -1,6 +1,7 @@
 // Shared helpers of libscipnp (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -33,8 +34,8 @@ inline int check_launch(const char* what) {
 }
 
 // launch counter (per process); the solver reports it as `gpu_launches`
-extern long long g_launches;
-inline void count_launch(int n = 1) { g_launches += n; }
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int num_sms();
 

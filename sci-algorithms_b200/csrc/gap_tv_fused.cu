@@ -80,7 +80,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 // generic tiled float32 tensor map (shared with gap_tv_ws.cu)
 int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const unsigned long long* dims,
-                        const unsigned long long* strides_bytes, const unsigned* box, int l2_promotion_128) {
+                        const unsigned long long* strides_bytes, const unsigned* box, int l2_promotion_128, int swizzle128) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return SCIPNP_ECUDA; }
     cuuint64_t d[5], s[4];
@@ -88,7 +88,7 @@ int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const unsi
     for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      l2_promotion_128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(rank %d) failed with CUresult %d", rank, (int)r); return SCIPNP_ECUDA; }

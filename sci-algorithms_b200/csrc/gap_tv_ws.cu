@@ -11,7 +11,7 @@ namespace scipnp {
 using namespace wsk;
 
 int make_tensor_map_f32(CUtensorMap* tm, const float* base, int rank, const unsigned long long* dims,
-                        const unsigned long long* strides_bytes, const unsigned* box, int l2_promotion_128);
+                        const unsigned long long* strides_bytes, const unsigned* box, int l2_promotion_128, int swizzle128 = 0);
 
 namespace {
 
@@ -112,25 +112,23 @@ bool fused_ws_supported(const FusedArgs& a) {
     return true;
 }
 
-// owned pixels per group and row segments per strip: one CTA per SM, as few waves as possible, long segments
-static void ws_split(int B, int H, int W, int Q, int R, int* own_out, int* nseg_out) {
+// Owned pixels per group and grid size.  The kernel deals the (batch x strips x charged rows) units out evenly
+// (WsSegIter), so the grid is one CTA per SM on large scenes; small scenes get segments of about 16 rows.
+static void ws_split(int B, int H, int W, int Q, int* own_out, int* grid_out) {
     const int NGRP = ws_groups(Q), nsm = num_sms();
     long long best = -1;
-    int bown = OWN_MAX, bseg = 1;
+    int bown = OWN_MAX, bgrid = 1;
     for (int own = OWN_MAX; own >= 32; own -= 4) {
         const int ngroups = (W + own - 1) / own, nstrips = (ngroups + NGRP - 1) / NGRP;
-        const int maxseg = H / 8 > 1 ? H / 8 : 1;
-        for (int nseg = 1; nseg <= maxseg && nseg <= 4096; ++nseg) {
-            const long long ctas = (long long)B * nstrips * nseg;
-            const long long waves = (ctas + nsm - 1) / nsm;
-            const long long rows = (H + nseg - 1) / nseg + 2 * R + 8;       // steps per CTA incl. warm-up, drain, fill
-            const long long cost = waves * rows;
-            if (best < 0 || cost < best) { best = cost; bown = own; bseg = nseg; }
-            if (waves > 1 && ctas > 8LL * nsm) break;
-        }
+        const long long total = (long long)B * nstrips * (H + kWsSegCost);
+        long long grid = total / 32;
+        if (grid > nsm) grid = nsm;
+        if (grid < 1) grid = 1;
+        const long long per_cta = (total + grid - 1) / grid;
+        if (best < 0 || per_cta < best) { best = per_cta; bown = own; bgrid = (int)grid; }
     }
     *own_out = bown;
-    *nseg_out = bseg;
+    *grid_out = bgrid;
 }
 
 int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
@@ -146,16 +144,14 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
     p.tv_w = (float)a.tv_weight;
     p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C;
     p.phi_batched = a.phi_batched ? 1 : 0;
-    int own = OWN_MAX, nseg = 1;
-    ws_split(a.B, a.H, a.W, Q, R, &own, &nseg);
+    int own = OWN_MAX, grid = 1;
+    ws_split(a.B, a.H, a.W, Q, &own, &grid);
     if (const char* e = getenv("SCIPNP_WS_OWN")) { int v = atoi(e); if (v >= 4 && v <= OWN_MAX && v % 4 == 0) own = v; }
-    if (const char* e = getenv("SCIPNP_WS_NSEG")) { int v = atoi(e); if (v >= 1 && v <= a.H) nseg = v; }
+    if (const char* e = getenv("SCIPNP_WS_GRID")) { int v = atoi(e); if (v >= 1) grid = v; }
     p.own = own;
-    p.nseg = nseg;
     p.ngroups = (a.W + own - 1) / own;
     p.nstrips = (p.ngroups + ws_groups(Q) - 1) / ws_groups(Q);
-    const long long ctas = (long long)a.B * p.nstrips * nseg;
-    if (ctas > 0x7fffffffLL) { set_error("scene too large for one launch"); return SCIPNP_EINVAL; }
+    const long long ctas = grid;
     MapKey key{a.x_in, a.x_out, a.Phi, a.y, a.mode == MODE_GAP_ACC ? a.y1_in : nullptr, a.Phi_sum,
                a.B, a.H, a.W, a.C, own, p.phi_batched};
     alignas(64) WsMaps maps;
@@ -196,7 +192,7 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
             for (size_t i = dur.size() > 6 ? dur.size() - 6 : 0; i < dur.size(); ++i) fprintf(stderr, " %lld:%lld", dur[i].second, dur[i].first);
             fprintf(stderr, "\n");
             for (long long cta : {0LL, ctas / 2, ctas - 1}) {
-                fprintf(stderr, "[ws prof] cta %lld own=%d nseg=%d grid=%lld\n", cta, own, nseg, ctas);
+                fprintf(stderr, "[ws prof] cta %lld own=%d grid=%lld\n", cta, own, ctas);
                 for (int w = 0; w < nwarp; ++w) {
                     const long long* r = &h[((size_t)cta * nwarp + w) * 4];
                     if (w < ncw) fprintf(stderr, "  consumer %2d: total %9lld  wait f_full %9lld  wait out_empty %9lld\n", w, r[0], r[1], r[2]);

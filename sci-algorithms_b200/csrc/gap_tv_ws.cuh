@@ -50,8 +50,7 @@ struct WsParams {
     int B, H, W, C;
     int own;                      // owned pixels per group (multiple of 4, <= OWN_MAX)
     int ngroups;                  // ceil(W / own)
-    int nstrips;                  // ceil(ngroups / NGRP): column strips (CTAs across the image)
-    int nseg;                     // row segments per strip
+    int nstrips;                  // ceil(ngroups / NGRP): column strips
     int phi_batched;
     long long* prof;              // optional [grid][warps][4] cycle counters (SCIPNP_WS_PROF), else null
 };
@@ -112,6 +111,19 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or about `ns`
+// nanoseconds have passed (no issue slots burnt while waiting)
+__device__ __forceinline__ bool mbar_try_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+
 __device__ __forceinline__ P2 shfl_dn2(P2 a) {
     return make_float2(__shfl_down_sync(0xffffffffu, a.x, 1), __shfl_down_sync(0xffffffffu, a.y, 1));
 }
@@ -143,9 +155,10 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
     constexpr bool FAST = PATH != 0;          // no row masks
     constexpr bool PXM = PATH != 1;           // pixel masks
     P2 o_new[2] = {f_new[0], f_new[1]};
-#ifdef WS_EXP
+#ifndef WS_EXP
+#define WS_EXP 0          // timing experiments (bit flags; results are meaningless): 1 independent stages, 2 no out-tile
+#endif                    // stores, 4 no energies, 8 no shuffles
     P2 o_last[2] = {f_new[0], f_new[1]};
-#endif
     P2 pi0[2], pi1[2];
     const P2 z = splat(0.f);
     pi0[0] = z; pi0[1] = z; pi1[0] = z; pi1[1] = z;              // p^0 = 0
@@ -163,11 +176,9 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
         } else {
             wm2 = c.w2;
         }
-#ifdef WS_EXP
-        if (FAST && (WS_EXP == 1 || (WS_EXP == 2 && i == R / 2))) { o_new[0] = f_new[0]; o_new[1] = f_new[1]; }
-#endif
+        if (FAST && (WS_EXP & 1)) { o_new[0] = f_new[0]; o_new[1] = f_new[1]; }
         // right neighbour of B in the new row: the next lane's A
-        const P2 o_rb = shfl_dn2(o_new[0]);
+        const P2 o_rb = (WS_EXP & 8) ? o_new[0] : shfl_dn2(o_new[0]);
         P2 g1[2], g0[2];
         g1[0] = fma2(S.o_prev[i][0], c.mone2, S.o_prev[i][1]);     // out_i(u, B) - out_i(u, A)
         g1[1] = S.g1b[i];
@@ -177,27 +188,33 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
             g0[q] = fma2(S.o_prev[i][q], c.mone2, o_new[q]);
             if (!FAST) g0[q] = mul2(g0[q], md2);
             nrm[q] = sqrt2(fma2(g0[q], g0[q], mul2(g1[q], g1[q])));
-            P2 r = rcp2(fma2(nrm[q], c.tvc2, c.one2));
-            if (PXM) r = mul2(r, m2);
-            pn0[q] = mul2(fma2(g0[q], c.mtau2, pi0[q]), r);
-            pn1[q] = mul2(fma2(g1[q], c.mtau2, pi1[q]), r);
+        }
+        P2 r[2];
+        r[0] = rcp2(fma2(nrm[0], c.tvc2, c.one2));
+        r[1] = rcp2(fma2(nrm[1], c.tvc2, c.one2));
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (PXM) r[q] = mul2(r[q], m2);
+            if (i == 0) {                                  // p^0 = 0: p^1 = (-tau*r) * g
+                const P2 rt = mul2(r[q], c.mtau2);
+                pn0[q] = mul2(g0[q], rt);
+                pn1[q] = mul2(g1[q], rt);
+            } else {
+                pn0[q] = mul2(fma2(g0[q], c.mtau2, pi0[q]), r[q]);
+                pn1[q] = mul2(fma2(g1[q], c.mtau2, pi1[q]), r[q]);
+            }
         }
         // D(p^{i+1})(u) = (p0(u-1) - p0(u)) + (p1(u, left) - p1(u)); the left neighbour of A is the previous lane's B
-        const P2 p1l_a = shfl_up2(pn1[1]);
+        const P2 p1l_a = (WS_EXP & 8) ? pn1[1] : shfl_up2(pn1[1]);
         P2 d[2];
         d[0] = add2(fma2(pn0[0], c.mone2, S.P0[i][0]), fma2(pn1[0], c.mone2, p1l_a));
         d[1] = add2(fma2(pn0[1], c.mone2, S.P0[i][1]), fma2(pn1[1], c.mone2, pn1[0]));
         // energies: w*|grad out_i|(u) belongs to iteration i, D(p^{i+1})(u)^2 to iteration i+1
-#if defined(WS_EXP) && WS_EXP == 4
-        if (!FAST)
-#endif
-        {
+        if (!(FAST && (WS_EXP & 4))) {
         S.en[i] = fma2(nrm[0], wm2, S.en[i]);
         S.en[i] = fma2(nrm[1], wm2, S.en[i]);
         }
-#if defined(WS_EXP) && WS_EXP == 4
-        if (!FAST)
-#endif
+        if (!(FAST && (WS_EXP & 4)))
         if (i + 1 < R) {
             if (FAST) {
                 S.en[i + 1] = fma2(d[0], d[0], S.en[i + 1]);
@@ -221,14 +238,10 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
             S.P1[i][q] = pn1[q];
             S.o_prev[i][q] = o_new[q];
             o_new[q] = o_next;
-#ifdef WS_EXP
-            o_last[q] = add2(o_last[q], o_next);
-#endif
+            if (WS_EXP & 1) o_last[q] = add2(o_last[q], o_next);
         }
     }
-#ifdef WS_EXP
-    if (FAST && (WS_EXP == 1 || WS_EXP == 2)) { o_new[0] = o_last[0]; o_new[1] = o_last[1]; }
-#endif
+    if (FAST && (WS_EXP & 1)) { o_new[0] = o_last[0]; o_new[1] = o_last[1]; }
 #pragma unroll
     for (int i = R - 1; i > 0; --i) { S.fd[i][0] = S.fd[i - 1][0]; S.fd[i][1] = S.fd[i - 1][1]; }
     S.fd[0][0] = f_new[0];
@@ -236,6 +249,43 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
     o_out[0] = o_new[0];
     o_out[1] = o_new[1];
 }
+
+// Work of one CTA: the scene is (batch x column strips) strips of H rows laid end to end, every strip charged
+// kSegCost extra units in front of its rows; a CTA takes `per_cta` consecutive units, i.e. a few row segments of
+// neighbouring strips (one or two on large scenes).  No wave quantisation: every SM gets the same share.
+constexpr int kWsSegCost = 16;    // cost of starting a row segment, in rows (warm-up + drain rows, pipeline fill)
+template <int R>
+struct WsSegIter {
+    long long unit, unit_end;
+    int Hv, H, nstrips;
+    int b, strip, r0, r1, rs, t_end, nblk;      // current segment
+    __device__ WsSegIter(const WsParams& p, int per_cta_unused = 0) {
+        H = p.H; Hv = p.H + kWsSegCost; nstrips = p.nstrips;
+        const long long total = (long long)p.B * p.nstrips * Hv;
+        const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
+        unit = (long long)blockIdx.x * per_cta;
+        unit_end = unit + per_cta < total ? unit + per_cta : total;
+    }
+    __device__ bool next() {
+        while (unit < unit_end) {
+            const int s = (int)(unit / Hv);
+            const int v0 = (int)(unit - (long long)s * Hv);
+            const long long left = unit_end - unit;
+            const int v1 = (long long)(Hv - v0) < left ? Hv : v0 + (int)left;
+            unit += v1 - v0;
+            r0 = v0 - kWsSegCost > 0 ? v0 - kWsSegCost : 0;
+            r1 = v1 - kWsSegCost;
+            if (r1 <= r0) continue;                                  // only charge units: no rows here
+            b = s / nstrips;
+            strip = s - b * nstrips;
+            rs = r0 - R > 0 ? r0 - R : 0;
+            t_end = r1 + R;                                          // steps t in [rs, t_end)
+            nblk = (t_end - rs + WRB - 1) / WRB;
+            return true;
+        }
+        return false;
+    }
+};
 
 // MODE: MODE_GAP_ACC or MODE_GAP_PLAIN.  Q = C/2 channel pairs.
 template <int R, int MODE, int Q>
@@ -265,23 +315,32 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
     }
     __syncthreads();
 
-    // ---- this CTA's work: one row segment of one column strip of one batch element
     const int H = p.H, W = p.W, own = p.own;
-    int bid = blockIdx.x;
-    const int seg = bid % p.nseg; bid /= p.nseg;
-    const int strip = bid % p.nstrips;
-    const int b = bid / p.nstrips;
-    const int r0 = (int)((long long)H * seg / p.nseg), r1 = (int)((long long)H * (seg + 1) / p.nseg);
-    const int rs = max(0, r0 - R), t_end = r1 + R;                 // steps t in [rs, t_end)
-    const int nblk = (t_end - rs + WRB - 1) / WRB;
-    const int group0 = strip * NGRP;
-    const int rowc0 = b * H;                                        // row coordinate of the batch element
-    const int phirow0 = p.phi_batched ? b * H : 0;
+    // Every role walks the same sequence of (segment, block) pairs; `gb` counts the blocks of all segments so far and
+    // gives the ring slot and the mbarrier phase.
 
     if (warp < CW) {
         // =================================== consumers ===================================
         const int gi = warp / Q, q = warp - gi * Q;
-        const int grp = group0 + gi;
+        // f tile: [WRB][NGRP][Q][GW][2] floats; this lane reads 16 bytes (A.c0 A.c1 B.c0 B.c1)
+        const uint32_t f_lane = smem_base + L.f_off + ((gi * Q + q) * GW + 2 * lane) * 8;
+        constexpr int F_ROW = NGRP * Q * GW * 8;
+        // out tile: [WRB][NGRP] sub-tiles of [K][own][4] floats; chunk k = q/2, half h = q%2
+        const int kq = q >> 1, hq = q & 1;
+        const uint32_t o_lane = smem_base + L.out_off + gi * L.out_sub + ((kq * own + 2 * (lane - HALO / 2)) * 4 + 2 * hq) * 4;
+        constexpr int O_ROW = NGRP * L.out_sub;
+        WsConst sc;
+        sc.mone2 = splat(-1.f); sc.mtau2 = splat(-0.25f); sc.tvc2 = splat(p.tv_c); sc.one2 = splat(1.f);
+        sc.w2 = splat(p.tv_w); sc.tvw = p.tv_w;
+        sc.H = H;
+        long long pw0 = 0, pw1 = 0;
+        const long long pstart = p.prof ? clock64() : 0;
+        int gb = 0;
+        WsSegIter<R> it(p);
+#pragma unroll 1
+        while (it.next()) {
+        const int r0 = it.r0, r1 = it.r1, rs = it.rs, t_end = it.t_end, nblk = it.nblk, b = it.b;
+        const int grp = it.strip * NGRP + gi;
         const bool grp_live = grp < p.ngroups;
         const int base = grp * own - HALO;                          // pixel of lane 0's A
         const int pxa = base + 2 * lane;
@@ -296,30 +355,18 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
 #pragma unroll
             for (int k2 = 0; k2 < 2; ++k2) { S.o_prev[i][k2] = z; S.P0[i][k2] = z; S.P1[i][k2] = z; S.fd[i][k2] = z; }
         }
-        WsConst sc;
-        sc.mone2 = splat(-1.f); sc.mtau2 = splat(-0.25f); sc.tvc2 = splat(p.tv_c); sc.one2 = splat(1.f);
-        sc.w2 = splat(p.tv_w); sc.tvw = p.tv_w;
         sc.pair_in = pair_in ? 1.f : 0.f;
         sc.right_in = (pair_in && pxa + 2 < W) ? 1.f : 0.f;
-        sc.rs = rs; sc.r0 = r0; sc.r1 = r1; sc.H = H;
-        // f tile: [WRB][NGRP][Q][GW][2] floats; this lane reads 16 bytes (A.c0 A.c1 B.c0 B.c1)
-        const uint32_t f_lane = smem_base + L.f_off + ((gi * Q + q) * GW + 2 * lane) * 8;
-        constexpr int F_ROW = NGRP * Q * GW * 8;
-        // out tile: [WRB][NGRP] sub-tiles of [K][own][4] floats; chunk k = q/2, half h = q%2
-        const int kq = q >> 1, hq = q & 1;
-        const uint32_t o_lane = smem_base + L.out_off + gi * L.out_sub + ((kq * own + 2 * (lane - HALO / 2)) * 4 + 2 * hq) * 4;
-        constexpr int O_ROW = NGRP * L.out_sub;
+        sc.rs = rs; sc.r0 = r0; sc.r1 = r1;
         const int fast_lo = r0 + R, fast_hi = min(r1, H) - 1;
-        long long pw0 = 0, pw1 = 0;
-        const long long pstart = p.prof ? clock64() : 0;
 #pragma unroll 1
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int fs = blk % NF, os = blk % NOUT;
+        for (int blk = 0; blk < nblk; ++blk, ++gb) {
+            const int fs = gb % NF, os = gb % NOUT;
             long long c0 = 0, c1 = 0;
             if (p.prof) c0 = clock64();
-            mbar_wait(bar_ffull + 8 * fs, (blk / NF) & 1);
+            mbar_wait(bar_ffull + 8 * fs, (gb / NF) & 1);
             if (p.prof) { c1 = clock64(); pw0 += c1 - c0; }
-            mbar_wait(bar_oempty + 8 * os, ((blk / NOUT) & 1) ^ 1);
+            mbar_wait(bar_oempty + 8 * os, ((gb / NOUT) & 1) ^ 1);
             if (p.prof) pw1 += clock64() - c1;
             const uint32_t fsrc = f_lane + fs * L.f_bytes;
             const uint32_t odst = o_lane + os * L.out_bytes;
@@ -334,11 +381,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     const P2 f_new[2] = {make_float2(fv.x, fv.y), make_float2(fv.z, fv.w)};
                     P2 o[2];
                     ws_step<R, PATH>(S, sc, t0 + j, f_new, o);
-#if defined(WS_EXP) && WS_EXP == 3
-                    if (own_lane && o[0].x == 123.456f) {
-#else
-                    if (own_lane) {
-#endif
+                    if (own_lane && (!(WS_EXP & 2) || o[0].x == 123.456f)) {
                         asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW), "f"(o[0].x), "f"(o[0].y) : "memory");
                         asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW + 16), "f"(o[1].x), "f"(o[1].y) : "memory");
                     }
@@ -372,11 +415,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 mbar_arrive(bar_fempty + 8 * fs);
             }
         }
-        if (p.prof && lane == 0) {
-            long long* pr = p.prof + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * 4;
-            pr[0] = clock64() - pstart; pr[1] = pw0; pr[2] = pw1; pr[3] = 0;
-        }
-        // energy partials: owned lanes only, one atomic per (channel, iteration)
+        // energy partials of this segment: owned lanes only, one atomic per (channel, iteration)
         if (p.flag != nullptr) {
 #pragma unroll
             for (int i = 0; i < R; ++i)
@@ -388,98 +427,123 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     if (lane == 0 && grp_live) atomicAdd(p.energy + ((size_t)b * C + 2 * q + ch) * R + i, (double)v);
                 }
         }
+        }   // segments
+        if (p.prof && lane == 0) {
+            long long* pr = p.prof + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * 4;
+            pr[0] = clock64() - pstart; pr[1] = pw0; pr[2] = pw1; pr[3] = 0;
+        }
     } else {
         // =================================== producers ===================================
         const int ptid = tid - CW * 32;                          // 0 .. NPROD*32-1
         constexpr int NPT = NPROD * 32;
         constexpr int NITEM = WRB * NGRP * GW;                   // (row, group, pixel) items per block
         constexpr uint32_t kTx = 2u * L.x_bytes + (MODE == MODE_GAP_ACC ? 3u : 2u) * NGRP * WRB * GW * 4;
-        auto issue = [&](int blk) {
-            if (blk < nblk && ptid == 0) {
-                const int slot = blk % NRAW;
-                const uint32_t dst = smem_base + slot * L.raw_bytes;
-                const uint32_t bar = bar_raw + 8 * slot;
-                const int row0 = rs + blk * WRB;
-                mbar_expect_tx(bar, kTx);
+        // TMA loads of block `blk` of the segment `sg` into raw slot `g % NRAW` (g = global block index)
+        auto issue = [&](const WsSegIter<R>& sg, int blk, int g) {
+            const int slot = g % NRAW;
+            const uint32_t dst = smem_base + slot * L.raw_bytes;
+            const uint32_t bar = bar_raw + 8 * slot;
+            const int row0 = sg.rs + blk * WRB;
+            const int rowc = sg.b * H + row0, prow = (p.phi_batched ? sg.b * H : 0) + row0;
+            mbar_expect_tx(bar, kTx);
 #pragma unroll
-                for (int g = 0; g < NGRP; ++g) {
-                    const int px0 = (group0 + g) * own - HALO;
-                    tma_load_3d(dst + g * (WRB * GW * C * 4), &maps.x, 0, px0, rowc0 + row0, bar);
-                    tma_load_3d(dst + L.x_bytes + g * (WRB * GW * C * 4), &maps.phi, 0, px0, phirow0 + row0, bar);
-                    const uint32_t ds = dst + L.small_off + g * (WRB * GW * 4);
-                    tma_load_2d(ds, &maps.y, px0, rowc0 + row0, bar);
-                    if (MODE == MODE_GAP_ACC) tma_load_2d(ds + NGRP * WRB * GW * 4, &maps.y1, px0, rowc0 + row0, bar);
-                    tma_load_2d(ds + 2 * NGRP * WRB * GW * 4, &maps.ps, px0, phirow0 + row0, bar);
-                }
+            for (int g2 = 0; g2 < NGRP; ++g2) {
+                const int px0 = (sg.strip * NGRP + g2) * own - HALO;
+                tma_load_3d(dst + g2 * (WRB * GW * C * 4), &maps.x, 0, px0, rowc, bar);
+                tma_load_3d(dst + L.x_bytes + g2 * (WRB * GW * C * 4), &maps.phi, 0, px0, prow, bar);
+                const uint32_t ds = dst + L.small_off + g2 * (WRB * GW * 4);
+                tma_load_2d(ds, &maps.y, px0, rowc, bar);
+                if (MODE == MODE_GAP_ACC) tma_load_2d(ds + NGRP * WRB * GW * 4, &maps.y1, px0, rowc, bar);
+                tma_load_2d(ds + 2 * NGRP * WRB * GW * 4, &maps.ps, px0, prow, bar);
             }
+        };
+        // The loader (thread 0 of the producers) runs NRAW blocks ahead of the producers, across segment boundaries
+        WsSegIter<R> ld(p);
+        bool ld_live = ld.next();
+        int ld_blk = 0, ld_g = 0;
+        auto load_next = [&]() {                                  // thread ptid == 0 only
+            if (!ld_live) return;
+            issue(ld, ld_blk, ld_g);
+            ++ld_g;
+            if (++ld_blk == ld.nblk) { ld_blk = 0; ld_live = ld.next(); }
         };
         // The first producer warp is also the storer: whenever every consumer warp has finished the rows of an
         // output block, its lane 0 hands the owned pixels of the rows inside [r0, r1) to the TMA unit.  It polls
         // while it waits for the consumers (never blocks on the output ring), so the rings cannot deadlock.
         const bool storer = warp == CW;
-        int sblk = 0;                                             // next output block to store
+        WsSegIter<R> st(p);
+        bool st_live = st.next();
+        int st_blk = 0, st_g = 0;
         auto store_block = [&]() {                                // lane 0 of the storer warp
-            const int os = sblk % NOUT;
+            const int os = st_g % NOUT;
             const uint32_t src = smem_base + L.out_off + os * L.out_bytes;
             for (int j = 0; j < WRB; ++j) {
-                const int orow = rs + sblk * WRB + j - R;
-                if (orow >= r0 && orow < r1) {
-                    for (int g = 0; g < NGRP; ++g)
-                        if (group0 + g < p.ngroups)
-                            tma_store_4d(&maps.out, src + (j * NGRP + g) * L.out_sub, 0, (group0 + g) * own, 0, rowc0 + orow);
+                const int orow = st.rs + st_blk * WRB + j - R;
+                if (orow >= st.r0 && orow < st.r1) {
+                    for (int g2 = 0; g2 < NGRP; ++g2)
+                        if (st.strip * NGRP + g2 < p.ngroups)
+                            tma_store_4d(&maps.out, src + (j * NGRP + g2) * L.out_sub, 0, (st.strip * NGRP + g2) * own, 0, st.b * H + orow);
                 }
             }
             bulk_commit();
             bulk_wait_read0();
             mbar_arrive(bar_oempty + 8 * os);
         };
+        auto store_advance = [&]() {                              // whole storer warp
+            ++st_g;
+            if (++st_blk == st.nblk) { st_blk = 0; st_live = st.next(); }
+        };
         auto store_poll = [&]() {
-            if (sblk < nblk) {
+            if (st_live) {
                 int ready = 0;
-                if (lane == 0) ready = mbar_try(bar_ofull + 8 * (sblk % NOUT), (sblk / NOUT) & 1) ? 1 : 0;
+                if (lane == 0) ready = mbar_try(bar_ofull + 8 * (st_g % NOUT), (st_g / NOUT) & 1) ? 1 : 0;
                 ready = __shfl_sync(0xffffffffu, ready, 0);
                 if (ready) {
                     if (lane == 0) store_block();
                     __syncwarp();
-                    ++sblk;
+                    store_advance();
                 }
             }
         };
         long long pw0 = 0, pw1 = 0, pw2 = 0;
         const long long pstart = p.prof ? clock64() : 0;
-        issue(0);
-        issue(1);
+        if (ptid == 0) { load_next(); load_next(); }
         const float lam = p.lambda;
-        float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + (size_t)b * H * W : nullptr;
         // bank pattern of the lane-per-pixel 16-byte reads: pixels are C*4 bytes apart.  For K = 2, 6 every
         // other group of four lanes visits the chunk pairs in swapped order, for K = 4 the chunk index is
         // xor-ed with (pixel / 2) % 4; odd K is conflict-free as it is.
         const int lsw = (K % 4 == 2) ? ((lane >> 2) & 1) : (K % 8 == 4) ? ((lane >> 1) & 3) : 0;
+        int gb = 0;
+        WsSegIter<R> it(p);
 #pragma unroll 1
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int slot = blk % NRAW, fs = blk % NF;
+        while (it.next()) {
+        const int r0 = it.r0, r1 = it.r1, rs = it.rs, nblk = it.nblk;
+        const int group0 = it.strip * NGRP;
+        float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + (size_t)it.b * H * W : nullptr;
+#pragma unroll 1
+        for (int blk = 0; blk < nblk; ++blk, ++gb) {
+            const int slot = gb % NRAW, fs = gb % NF;
             long long c0 = 0, c1 = 0;
             if (p.prof) c0 = clock64();
-            mbar_wait(bar_raw + 8 * slot, (blk / NRAW) & 1);
+            mbar_wait(bar_raw + 8 * slot, (gb / NRAW) & 1);
             if (p.prof) { c1 = clock64(); pw0 += c1 - c0; }
             if (storer) {
                 store_poll();
                 for (;;) {
                     int ok = 0;
-                    if (lane == 0) ok = mbar_try(bar_fempty + 8 * fs, ((blk / NF) & 1) ^ 1) ? 1 : 0;
+                    if (lane == 0) ok = mbar_try_sleep(bar_fempty + 8 * fs, ((gb / NF) & 1) ^ 1, 256) ? 1 : 0;
                     if (__shfl_sync(0xffffffffu, ok, 0)) break;
                     store_poll();
-                    __nanosleep(32);
                 }
             } else {
-                mbar_wait(bar_fempty + 8 * fs, ((blk / NF) & 1) ^ 1);
+                mbar_wait(bar_fempty + 8 * fs, ((gb / NF) & 1) ^ 1);
             }
             if (p.prof) pw1 += clock64() - c1;
             const unsigned char* raw = smem_raw + slot * L.raw_bytes;
             unsigned char* fdst = smem_raw + L.f_off + fs * L.f_bytes;
 #pragma unroll 1
-            for (int it = ptid; it < NITEM; it += NPT) {
-                const int px = it & (GW - 1), g = (it / GW) % NGRP, j = it / (GW * NGRP);
+            for (int itx = ptid; itx < NITEM; itx += NPT) {
+                const int px = itx & (GW - 1), g = (itx / GW) % NGRP, j = itx / (GW * NGRP);
                 const int row = rs + blk * WRB + j;
                 const int gpx = (group0 + g) * own - HALO + px;
                 const bool in = (group0 + g) < p.ngroups && gpx >= 0 && gpx < W && row < H;
@@ -521,18 +585,19 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             if (p.prof) c0 = clock64();
             prod_bar();                              // every producer is done reading the raw slot
             if (p.prof) pw2 += clock64() - c0;
-            issue(blk + NRAW);
+            if (ptid == 0) load_next();
         }
+        }   // segments
         if (p.prof && lane == 0) {
             long long* pr = p.prof + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * 4;
             pr[0] = clock64() - pstart; pr[1] = pw0; pr[2] = pw1; pr[3] = pw2;
         }
         if (storer) {
-            while (sblk < nblk) {
-                mbar_wait(bar_ofull + 8 * (sblk % NOUT), (sblk / NOUT) & 1);
+            while (st_live) {
+                mbar_wait(bar_ofull + 8 * (st_g % NOUT), (st_g / NOUT) & 1);
                 if (lane == 0) store_block();
                 __syncwarp();
-                ++sblk;
+                store_advance();
             }
             if (lane == 0) bulk_wait0();
         }

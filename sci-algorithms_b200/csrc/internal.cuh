@@ -18,9 +18,17 @@ int launch_sq_err(const float* a, const float* b, size_t n_per_batch, int B, dou
 
 // tv_exact.cu
 size_t tv_workspace_bytes(int B, int H, int W, int C);
+// Row-tiled scenes: energies over rows [e_lo, e_hi) only, `reduce` (if set) sums the 2*B*C partial energies of
+// a dual iteration over the ranks before the stopping rule is applied (scipnp_energy_reduce_fn of scipnp.h).
+struct TvTiling {
+    int e_lo = 0, e_hi = 0;                       // e_hi == 0: every row
+    long long total_rows = 0;                     // rows of the whole scene (0: H)
+    int (*reduce)(double* dev, int n, void* stream, void* user) = nullptr;
+    void* user = nullptr;
+};
 int tv_chambolle_exact(const float* in, float* out, double weight, double eps, int T, int B, int H,
                        int W, int C, void* workspace, size_t ws_bytes, int* n_exec_dev,
-                       double* energy_dev, int energy_cap, cudaStream_t st);
+                       double* energy_dev, int energy_cap, cudaStream_t st, const TvTiling* tiling = nullptr);
 
 // gap_tv_fused.cu
 struct FusedArgs {
@@ -40,6 +48,11 @@ struct FusedArgs {
     // CASSI: Phi == nullptr and the coded aperture mask2d [H][mask_w] is read at offset step*c
     const float* mask2d; int cassi_step; int mask_w;
     int clip01;               // clip the TV output to [0,1]
+    // Row-tiled scenes: only rows [e_lo, e_hi) (the rows this rank owns) enter the TV energies, which the caller
+    // sums over the ranks before it applies the stopping rule.  e_hi == 0: every row.
+    int e_lo = 0, e_hi = 0;
+    bool accumulate_only = false;   // leave the energies in the workspace: no check, no reset (flag is ignored)
+    bool skip_clear = false;        // the workspace slot is already zero
 };
 bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
 bool fused_cassi_supported(int mode, int B, int H, int W, int C, int tv_iter_max);

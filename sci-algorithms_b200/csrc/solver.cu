@@ -11,6 +11,7 @@
 //              on the exact path, so results never depend on the path taken.
 //   fused = 0  exact path: projection kernel + per-iteration TV kernels.
 #include <math.h>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -144,7 +145,7 @@ int scipnp_solver_create(const scipnp_params* pp, scipnp_solver** out) {
     s->xbuf[0] = s->xa; s->xbuf[1] = s->xb;
     s->y1buf[0] = s->y1a; s->y1buf[1] = s->y1b;
     // exact-path workspace is allocated lazily (only the exact path or a rollback needs it)
-    s->launches0 = g_launches;
+    s->launches0 = g_launches.load();
     *out = s;
     return SCIPNP_OK;
 }
@@ -307,6 +308,11 @@ int scipnp_solver_step_async(scipnp_solver* s, int iters, void* stream) {
     if (!s->loaded) { set_error("scipnp_solver_step_async before scipnp_solver_load"); return SCIPNP_ESTATE; }
     cudaStream_t st = (cudaStream_t)stream;
     const scipnp_params& p = s->p;
+    if (s->has_orig && (long long)(s->iters_done + iters) * p.B > kPsnrCap) {
+        set_error("psnr_all holds %d values: %d iterations x %d measurements do not fit (run without X_orig)",
+                  kPsnrCap, s->iters_done + iters, p.B);
+        return SCIPNP_EINVAL;
+    }
     if (!s->use_fused)
         if (int e = ensure_exact_buffers(s)) return e;
     for (int i = 0; i < iters; ++i)
@@ -445,7 +451,7 @@ int scipnp_solver_admm_state(scipnp_solver* s, float** theta, float** b, float**
 
 int scipnp_solver_uses_fused(scipnp_solver* s) { return s && s->use_fused ? 1 : 0; }
 
-long long scipnp_solver_launch_count(scipnp_solver* s) { return s ? g_launches - s->launches0 : 0; }
+long long scipnp_solver_launch_count(scipnp_solver* s) { return s ? g_launches.load() - s->launches0 : 0; }
 
 // ---------------------------------------------------------------------------------------------
 // Row-tiled multi-GPU mode ("single UHD scene"): this handle holds rows
@@ -661,14 +667,19 @@ int scipnp_solver_run_tiled(scipnp_solver* s, int iters, int k, void* stream) {
     if (!s->tiled) { set_error("not a tiled solver"); return SCIPNP_ESTATE; }
     cudaStream_t st = (cudaStream_t)stream;
     for (int it = 0; it < iters; ++it) {
-        // the step after next overwrites the buffer the neighbours pulled from: by the second
-        // step after an exchange their acknowledgement must be in
-        if (s->ack_pending && k > 1 && (it % k) == 1)
+        // The neighbours pull from the buffer the state was in at the last exchange.  The fused step ping-pongs, so
+        // it is the step after next that overwrites that buffer: their acknowledgement must be in by the second step
+        // after an exchange (k = 1: the next exchange waits for it).  The exact path projects in place, so there
+        // the very next step has to wait.
+        if (s->ack_pending && (!s->use_fused || (k > 1 && (it % k) == 1)))
             if (int e = tile_wait_ack(s, st)) return e;
         if (int e = scipnp_solver_step_async(s, 1, stream)) return e;
         if ((it + 1) % k == 0 || it + 1 == iters)
             if (int e = scipnp_solver_exchange(s, stream)) return e;
     }
+    // When the stream has drained the neighbours are done reading my buffers: a following load(), rollback or
+    // owned() copy may touch them without another rendezvous.
+    if (int e = tile_wait_ack(s, st)) return e;
     return SCIPNP_OK;
 }
 
@@ -685,6 +696,13 @@ int scipnp_solver_sync_error(scipnp_solver* s, int* timed_out, void* stream) {
 // The host-buffer entries keep their last solver handle: a second call with the same parameters
 // reuses its ~6 GB of device buffers instead of paying cudaMalloc/cudaFree again.
 static scipnp_solver* g_host_solver = nullptr;
+static std::mutex g_host_mu;      // the one-call entries share the cached handle: one caller at a time
+
+static bool same_params(const scipnp_params& a, const scipnp_params& b) {      // field by field: the struct has padding
+    return a.method == b.method && a.accelerate == b.accelerate && a.lambda == b.lambda && a.gamma == b.gamma &&
+           a.tv_weight == b.tv_weight && a.tv_eps == b.tv_eps && a.tv_iter_max == b.tv_iter_max && a.fused == b.fused &&
+           a.B == b.B && a.H == b.H && a.W == b.W && a.C == b.C && a.phi_batched == b.phi_batched && a.clip01 == b.clip01;
+}
 
 static int denoise_host(int method, const float* y, const float* Phi, const float* x0,
                         const float* X_orig, const scipnp_params* p, int iters, float* x_out,
@@ -692,8 +710,9 @@ static int denoise_host(int method, const float* y, const float* Phi, const floa
     SCIPNP_REQUIRE(p && y && Phi && x_out, "null pointer");
     scipnp_params q = *p;
     q.method = method;
+    std::lock_guard<std::mutex> lock(g_host_mu);
     scipnp_solver* s = g_host_solver;
-    if (s && memcmp(&s->p, &q, sizeof(q)) != 0) {
+    if (s && !same_params(s->p, q)) {
         scipnp_solver_destroy(s);
         s = g_host_solver = nullptr;
     }
@@ -715,6 +734,7 @@ static int denoise_host(int method, const float* y, const float* Phi, const floa
 }
 
 int scipnp_host_release(void) {
+    std::lock_guard<std::mutex> lock(g_host_mu);
     if (g_host_solver) scipnp_solver_destroy(g_host_solver);
     g_host_solver = nullptr;
     return SCIPNP_OK;

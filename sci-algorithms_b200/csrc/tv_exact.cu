@@ -43,7 +43,7 @@ __device__ __forceinline__ void store_vec(float* p, const float* o) {
 template <int V>
 __global__ void __launch_bounds__(kTvThreads)
 tv_out_kernel(const float* __restrict__ f, const float* __restrict__ p0, const float* __restrict__ p1,
-              float* __restrict__ out, TvSlice* __restrict__ sl, int H, int W, int C) {
+              float* __restrict__ out, TvSlice* __restrict__ sl, int H, int W, int C, int e_lo, int e_hi) {
     extern __shared__ double sacc[];   // [C]
     const int WC = W * C, nvec = WC / V;
     const int b = blockIdx.z;
@@ -79,7 +79,7 @@ tv_out_kernel(const float* __restrict__ f, const float* __restrict__ p0, const f
                     if (has_left) d = __fadd_rn(d, lf[i]);
                     if (active[i]) {
                         ov[i] = __fadd_rn(fv[i], d);
-                        acc[i] += (double)__fmul_rn(d, d);
+                        if (r >= e_lo && r < e_hi) acc[i] += (double)__fmul_rn(d, d);
                     }
                 }
                 store_vec<V>(out + o, ov);
@@ -97,7 +97,7 @@ tv_out_kernel(const float* __restrict__ f, const float* __restrict__ p0, const f
 template <int V>
 __global__ void __launch_bounds__(kTvThreads)
 tv_dual_kernel(const float* __restrict__ outi, float* __restrict__ p0, float* __restrict__ p1,
-               TvSlice* __restrict__ sl, int H, int W, int C, float tau, float tau_over_w) {
+               TvSlice* __restrict__ sl, int H, int W, int C, float tau, float tau_over_w, int e_lo, int e_hi) {
     extern __shared__ double sacc[];
     const int WC = W * C, nvec = WC / V;
     const int b = blockIdx.z;
@@ -133,7 +133,7 @@ tv_dual_kernel(const float* __restrict__ outi, float* __restrict__ p0, float* __
                     float g1 = has_right ? __fsub_rn(rt[i], cur[i]) : 0.f;
                     float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(g0, g0), __fmul_rn(g1, g1)));
                     if (active[i]) {
-                        acc[i] += (double)nrm;
+                        if (r >= e_lo && r < e_hi) acc[i] += (double)nrm;
                         float den = __fadd_rn(__fmul_rn(nrm, tau_over_w), 1.f);
                         a0[i] = __fdiv_rn(__fsub_rn(a0[i], __fmul_rn(tau, g0)), den);
                         a1[i] = __fdiv_rn(__fsub_rn(a1[i], __fmul_rn(tau, g1)), den);
@@ -170,6 +170,16 @@ __global__ void tv_check_kernel(TvSlice* __restrict__ sl, int nslice, int i, dou
     sl[s] = t;
 }
 
+// gather / scatter of the per-slice partial energies around the cross-rank sum (row-tiled scenes)
+__global__ void tv_acc_gather_kernel(const TvSlice* __restrict__ sl, int nslice, double* __restrict__ buf) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslice) { buf[2 * s] = sl[s].acc_d; buf[2 * s + 1] = sl[s].acc_n; }
+}
+__global__ void tv_acc_scatter_kernel(TvSlice* __restrict__ sl, int nslice, const double* __restrict__ buf) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < nslice) { sl[s].acc_d = buf[2 * s]; sl[s].acc_n = buf[2 * s + 1]; }
+}
+
 __global__ void tv_finish_kernel(const TvSlice* __restrict__ sl, int nslice, int* __restrict__ n_exec,
                                  int* __restrict__ flag, int n_iter_max) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,14 +197,15 @@ size_t tv_workspace_bytes(int B, int H, int W, int C) {
     size_t field = (size_t)B * H * W * C * sizeof(float);
     field = (field + 255) & ~(size_t)255;
     size_t slices = ((size_t)B * C * sizeof(TvSlice) + 255) & ~(size_t)255;
-    return 2 * field + slices;
+    size_t accbuf = ((size_t)B * C * 2 * sizeof(double) + 255) & ~(size_t)255;    // staging of the cross-rank energy sum
+    return 2 * field + slices + accbuf;
 }
 
 // Runs the whole denoiser on `st`.  full_energy: also evaluate the (dead) dual
 // update of the last iteration so that E and n_exec of that iteration exist.
 int tv_chambolle_exact(const float* in, float* out, double weight, double eps, int T, int B, int H,
                        int W, int C, void* workspace, size_t ws_bytes, int* n_exec_dev,
-                       double* energy_dev, int energy_cap, cudaStream_t st) {
+                       double* energy_dev, int energy_cap, cudaStream_t st, const TvTiling* tiling) {
     if (ws_bytes < tv_workspace_bytes(B, H, W, C)) {
         set_error("tv workspace too small: %zu < %zu", ws_bytes, tv_workspace_bytes(B, H, W, C));
         return SCIPNP_EINVAL;
@@ -205,6 +216,11 @@ int tv_chambolle_exact(const float* in, float* out, double weight, double eps, i
     float* p1 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + field);
     TvSlice* sl = reinterpret_cast<TvSlice*>(reinterpret_cast<char*>(workspace) + 2 * field);
     const int nslice = B * C;
+    double* accbuf = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 2 * field +
+                                               (((size_t)nslice * sizeof(TvSlice) + 255) & ~(size_t)255));
+    const int e_lo = (tiling && tiling->e_hi > 0) ? tiling->e_lo : 0;
+    const int e_hi = (tiling && tiling->e_hi > 0) ? tiling->e_hi : H;
+    const double size = (double)((tiling && tiling->total_rows > 0) ? tiling->total_rows : H) * W;
     SCIPNP_CUDA(cudaMemsetAsync(workspace, 0, 2 * field + (size_t)nslice * sizeof(TvSlice), st));
     if (energy_dev && energy_cap > 0) {
         size_t n = (size_t)nslice * energy_cap;
@@ -220,28 +236,41 @@ int tv_chambolle_exact(const float* in, float* out, double weight, double eps, i
     const float tau = 0.25f;
     const float tow = (float)(0.25 / weight);
     const unsigned cgrid = (unsigned)ceil_div_ll(nslice, 128);
+    // sum the partial energies of this dual iteration over the ranks (row-tiled scenes)
+    auto reduce_acc = [&]() -> int {
+        if (!tiling || !tiling->reduce) return SCIPNP_OK;
+        tv_acc_gather_kernel<<<cgrid, 128, 0, st>>>(sl, nslice, accbuf);
+        if (int rc = tiling->reduce(accbuf, 2 * nslice, (void*)st, tiling->user)) {
+            set_error("energy reduction callback failed with %d", rc);
+            return SCIPNP_ESTATE;
+        }
+        tv_acc_scatter_kernel<<<cgrid, 128, 0, st>>>(sl, nslice, accbuf);
+        count_launch(2);
+        return SCIPNP_OK;
+    };
     if (T <= 1) {
         SCIPNP_CUDA(cudaMemcpyAsync(out, in, nelem * sizeof(float), cudaMemcpyDeviceToDevice, st));
         if (T == 1 && want_stats) {   // E_0 needs |grad f|
-            if (V == 4) tv_dual_kernel<4><<<grid, kTvThreads, smem, st>>>(in, p0, p1, sl, H, W, C, tau, tow);
-            else tv_dual_kernel<1><<<grid, kTvThreads, smem, st>>>(in, p0, p1, sl, H, W, C, tau, tow);
-            tv_check_kernel<<<cgrid, 128, 0, st>>>(sl, nslice, 0, weight, eps, (double)H * W, energy_dev, energy_cap);
+            if (V == 4) tv_dual_kernel<4><<<grid, kTvThreads, smem, st>>>(in, p0, p1, sl, H, W, C, tau, tow, e_lo, e_hi);
+            else tv_dual_kernel<1><<<grid, kTvThreads, smem, st>>>(in, p0, p1, sl, H, W, C, tau, tow, e_lo, e_hi);
+            if (int e = reduce_acc()) return e;
+            tv_check_kernel<<<cgrid, 128, 0, st>>>(sl, nslice, 0, weight, eps, size, energy_dev, energy_cap);
             count_launch(2);
         }
     }
     for (int i = 0; i < T && T > 1; ++i) {
         const float* src = in;
         if (i > 0) {
-            if (V == 4) tv_out_kernel<4><<<grid, kTvThreads, smem, st>>>(in, p0, p1, out, sl, H, W, C);
-            else tv_out_kernel<1><<<grid, kTvThreads, smem, st>>>(in, p0, p1, out, sl, H, W, C);
+            if (V == 4) tv_out_kernel<4><<<grid, kTvThreads, smem, st>>>(in, p0, p1, out, sl, H, W, C, e_lo, e_hi);
+            else tv_out_kernel<1><<<grid, kTvThreads, smem, st>>>(in, p0, p1, out, sl, H, W, C, e_lo, e_hi);
             count_launch();
             src = out;
         }
         if (i == T - 1 && !want_stats) break;      // last dual update is dead code
-        if (V == 4) tv_dual_kernel<4><<<grid, kTvThreads, smem, st>>>(src, p0, p1, sl, H, W, C, tau, tow);
-        else tv_dual_kernel<1><<<grid, kTvThreads, smem, st>>>(src, p0, p1, sl, H, W, C, tau, tow);
-        tv_check_kernel<<<cgrid, 128, 0, st>>>(sl, nslice, i, weight, eps, (double)H * W,
-                                               energy_dev, energy_cap);
+        if (V == 4) tv_dual_kernel<4><<<grid, kTvThreads, smem, st>>>(src, p0, p1, sl, H, W, C, tau, tow, e_lo, e_hi);
+        else tv_dual_kernel<1><<<grid, kTvThreads, smem, st>>>(src, p0, p1, sl, H, W, C, tau, tow, e_lo, e_hi);
+        if (int e = reduce_acc()) return e;
+        tv_check_kernel<<<cgrid, 128, 0, st>>>(sl, nslice, i, weight, eps, size, energy_dev, energy_cap);
         count_launch(2);
     }
     if (n_exec_dev) {

@@ -1,0 +1,112 @@
+"""GPU tests of the row-tiled multi-GPU mode with the transport bench.py measures: "p2p" -- CUDA-IPC mapped
+neighbour buffers, halo rows pulled by tile_exchange_kernel, device-side flags (csrc/solver.cu).
+
+Several ranks share cuda:0 here (one process per rank, gloo rendezvous, CUDA IPC between the processes), so the
+whole flag protocol, the lazy acknowledgements and the pull kernel run exactly as on a multi-GPU box; only the
+wire is missing.  Every test fails if the solver fell back to another transport.
+
+Checked: tiled result == single-GPU solve of the same scene (owned rows never see a seam) for refresh periods
+k = 1, 2, 3, two and three ranks, two runs back to back (halos must be fresh at a run boundary), the exact path
+(in-place projection: the acknowledgement must be awaited before the very next step), and a forced early stop
+(collective rollback to the exact path in the middle of a p2p run).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import scipnp
+    return scipnp
+
+
+def _worker(rank, world, port, H, W, C, iters, k, fused, tv_eps, method, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from scipnp.tiled import TiledSolver
+        from scipnp import synth
+        meas, mask, _ = synth.make_cacti(H, W, C, 1, cfg=21)
+        y = meas[:, :, 0] / np.float32(255.)
+        ts = TiledSolver(H, W, C, rank, world, tv_weight=0.3, tv_iter_max=5, exchange_every=k, transport="p2p",
+                         fused=fused, tv_eps=tv_eps, method=method)
+        assert ts.transport == "p2p", "fell back to %s" % ts.transport
+        ts.load(torch.from_numpy(y[ts.row_lo:ts.row_hi]).cuda(), torch.from_numpy(mask[ts.row_lo:ts.row_hi]).cuda())
+        ts.run(iters // 2)
+        ts.run(iters - iters // 2)             # two runs: halos must be fresh at a run boundary
+        np.save(os.path.join(out_dir, "x_%d.npy" % rank), ts.result().cpu().numpy())
+        np.save(os.path.join(out_dir, "meta_%d.npy" % rank), np.array([ts.refined_iters, int(ts.uses_fused)]))
+        ts.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def _tiled(tmp_path, world, H, W, C, iters, k, fused=True, tv_eps=2e-4, method="gap"):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(world, port, H, W, C, iters, k, fused, tv_eps, method, str(tmp_path)), nprocs=world, join=True)
+    got = np.concatenate([np.load(tmp_path / ("x_%d.npy" % r)) for r in range(world)], axis=0)
+    meta = np.stack([np.load(tmp_path / ("meta_%d.npy" % r)) for r in range(world)])
+    return got, meta
+
+
+def _single(H, W, C, iters, fused=True, tv_eps=2e-4, method="gap"):
+    from scipnp import synth, Solver
+    meas, mask, _ = synth.make_cacti(H, W, C, 1, cfg=21)
+    y = meas[:, :, 0] / np.float32(255.)
+    with Solver(1, H, W, C, method=method, tv_weight=0.3, tv_iter_max=5, fused=fused, tv_eps=tv_eps) as so:
+        so.load(y[None], mask)
+        so.run(iters // 2)
+        so.run(iters - iters // 2)
+        return so.get_x()[0], so.refined_iters
+
+
+@pytest.mark.parametrize("world,k", [(2, 1), (2, 2), (2, 3), (3, 1), (3, 2)])
+def test_p2p_tiled_equals_single_gpu(sp, tmp_path, world, k):
+    H, W, C, iters = 64 * world + 8, 128, 8, 7
+    got, meta = _tiled(tmp_path, world, H, W, C, iters, k)
+    ref, refined = _single(H, W, C, iters)
+    assert refined == 0 and (meta[:, 0] == 0).all() and (meta[:, 1] == 1).all()
+    assert float(np.abs(got - ref).max()) <= 1e-6
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_p2p_tiled_exact_path(sp, tmp_path, k):
+    """fused = False: the projection runs in place, so the step right after an exchange must wait for the
+    neighbours' acknowledgement (it used to overwrite rows that were still being pulled)."""
+    H, W, C, iters = 136, 128, 8, 5
+    got, meta = _tiled(tmp_path, 2, H, W, C, iters, k, fused=False)
+    ref, _ = _single(H, W, C, iters, fused=False)
+    assert (meta[:, 1] == 0).all()
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_p2p_tiled_rollback_in_the_middle_of_a_run(sp, tmp_path):
+    """A huge eps makes the early stop fire: every rank rolls back and redoes the run on the exact path over the
+    same p2p links.  With the [C][T] energies summed over the owned rows of all ranks the stopping decisions are
+    those of the single-GPU solve, so the results agree."""
+    H, W, C, iters = 136, 128, 8, 4
+    got, meta = _tiled(tmp_path, 2, H, W, C, iters, 2, tv_eps=0.5)
+    ref, refined = _single(H, W, C, iters, tv_eps=0.5)
+    assert refined == iters and (meta[:, 0] == iters).all()
+    assert float(np.abs(got - ref).max()) <= 2e-6
+
+
+def test_p2p_tiled_config5_width(sp, tmp_path):
+    """Two ranks on a 3840-wide, 24-channel band (the bench's tile shape, fewer rows), k = 2."""
+    H, W, C, iters = 96, 3840, 24, 4
+    got, meta = _tiled(tmp_path, 2, H, W, C, iters, 2)
+    ref, _ = _single(H, W, C, iters)
+    assert (meta[:, 1] == 1).all()
+    assert float(np.abs(got - ref).max()) <= 1e-6
