@@ -209,6 +209,120 @@ def run_reference(args):
     emit(line)
 
 
+# -- the other BASELINE configurations (1-4): per-iteration time, roofline fraction, parity ------------------
+
+def _time_run(torch, run, iters, reps=5):
+    """ms per outer iteration: `run(iters)` timed with CUDA events, best of `reps`, after a warm-up run."""
+    run(iters)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run(iters)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / iters
+        best = ms if best is None else min(best, ms)
+    return best
+
+
+def measure_configs(torch, peak):
+    """BASELINE.json configs 1-4 on one GPU (the headline stays config 5).  For each: ms per outer iteration
+    over ITERS iterations of the device-resident solver, the algorithmic bytes of that shape against the
+    HBM peak, and parity against the oracle on the same seeded inputs for a few iterations (the
+    config-size 40-iteration parity runs live in tests/test_gpu_configs.py)."""
+    import scipnp
+    from scipnp import synth
+    from scipnp.engine import Solver
+    from oracle import pnp_sci as O
+    out = {}
+
+    def entry(name, workload, ms, nbytes, launches, parity, path):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"workload": workload, "ms_per_iteration": ms, "us_per_iteration": 1e3 * ms,
+                     "iterations_per_s": 1e3 / ms, "algorithmic_bytes_per_iteration": nbytes,
+                     "achieved_gbs": ach, "frac": ach / peak, "launches_per_iteration": launches,
+                     "path": path, "parity": parity}
+
+    def par(xg, xo, pag, pao, iters):
+        return {"max_abs_err": float(np.abs(xg - xo).max()),
+                "psnr_delta_db": float(np.abs(np.array(pag) - np.array(pao)).max()), "iterations": iters,
+                "tolerance": "max abs <= 1e-4, |dPSNR| <= 0.01 dB"}
+
+    # c1: GAP-TV 256x256x8, one measurement (pnp_sci_demo_kobe.py:82-98)
+    meas, mask, orig = synth.make_cacti(256, 256, 8, 1, cfg=1)
+    A, At = (lambda x: O.A_(x, mask)), (lambda v: O.At_(v, mask))
+    kw = dict(projmeth='gap', orig=orig, nframe=1, MAXB=255., _lambda=1, accelerate=True, denoiser='tv',
+              iter_max=10, tv_weight=0.3, tv_iter_max=5)
+    xo, _, _, _, pao = O.admmdenoise_cacti(meas, mask, A, At, **kw)
+    xg, _, _, _, pag = scipnp.admmdenoise_cacti(meas, mask, A, At, **kw)
+    with Solver(1, 256, 256, 8, method="gap", tv_weight=0.3, tv_iter_max=5) as so:
+        so.load(meas[None, :, :, 0] / np.float32(255.), mask)
+        l0 = so.launches
+        ms = _time_run(torch, so.run, ITERS)
+        lpi = (so.launches - l0) / (6. * ITERS)
+        path = "fused" if so.uses_fused else "exact"
+    entry("c1", "GAP-TV 256x256xCr=8, 1 measurement", ms, algorithmic_bytes(256, 256, 8), lpi,
+          par(xg, xo, pag, pao, 10), path)
+
+    # c2: ADMM-TV, the 28 coded frames of the six grayscale benchmarks as one batch with per-frame masks
+    F = 28
+    scenes = [synth.make_cacti(256, 256, 8, 1, cfg=20 + i) for i in range(F)]
+    yb = np.stack([m[:, :, 0] / np.float32(255.) for m, _, _ in scenes])
+    pb = np.stack([k for _, k, _ in scenes])
+    with Solver(F, 256, 256, 8, method="admm", gamma=0.01, tv_weight=0.3, tv_iter_max=5, phi_batched=True) as so:
+        so.load(yb, pb)
+        l0 = so.launches
+        ms = _time_run(torch, so.run, ITERS)
+        lpi = (so.launches - l0) / (6. * ITERS)
+        path = "fused" if so.uses_fused else "exact"
+    meas, mask, orig = scenes[0][0], scenes[0][1], scenes[0][2]
+    A, At = (lambda x: O.A_(x, mask)), (lambda v: O.At_(v, mask))
+    kw = dict(projmeth='admm', orig=orig, nframe=1, MAXB=255., _lambda=1, gamma=0.01, denoiser='tv',
+              iter_max=10, tv_weight=0.3, tv_iter_max=5)
+    xo, _, _, _, pao = O.admmdenoise_cacti(meas, mask, A, At, **kw)
+    xg, _, _, _, pag = scipnp.admmdenoise_cacti(meas, mask, A, At, **kw)
+    # ADMM: read theta, b, Phi (3NC) + y, Phi_sum (2N); write theta, b, x (3NC)
+    entry("c2", "ADMM-TV 28 coded frames 256x256xCr=8 (one batch, per-frame masks)", ms,
+          F * 4 * 256 * 256 * (6 * 8 + 2), lpi, par(xg, xo, pag, pao, 10), path)
+
+    # c3: GAP-TV Bayer 512x512x24 = four 256x256x24 sub-lattices with their own masks
+    y, Phi, orig = synth.make_bayer(512, 512, 24, cfg=3)
+    kw = dict(_lambda=1, accelerate=True, denoiser='tv', iter_max=3, tv_weight=0.1, tv_iter_max=5, X_orig=orig)
+    xo, _, _, pao = O.gap_denoise_bayer(y, Phi, **kw)
+    xg, _, _, pag = scipnp.gap_denoise_bayer(y, Phi, **kw)
+    sub = lambda a: np.stack([np.ascontiguousarray(a[i::2, j::2]) for i, j in ((0, 0), (0, 1), (1, 0), (1, 1))])
+    with Solver(4, 256, 256, 24, method="gap", tv_weight=0.1, tv_iter_max=5, phi_batched=True) as so:
+        so.load(sub(y), sub(Phi))
+        l0 = so.launches
+        ms = _time_run(torch, so.run, ITERS)
+        lpi = (so.launches - l0) / (6. * ITERS)
+        path = "fused" if so.uses_fused else "exact"
+    entry("c3", "GAP-TV Bayer 512x512xCr=24 (4 sub-lattices 256x256x24)", ms, 4 * algorithmic_bytes(256, 256, 24),
+          lpi, par(xg, xo, pag, pao, 3), path)
+
+    # c4: GAP-TV CASSI 256x256x28 bands, dispersion 2 px/band (canvas 256x310)
+    nband, step = 28, 2
+    y, m2, cube = synth.make_cassi(256, 256, nband, step=step, cfg=4)
+    Phi = O.cassi_shift_mask(m2, nband, step)
+    A, At = (lambda x: O.A_(x, Phi)), (lambda v: O.At_(v, Phi))
+    xo, _, _, pao = O.gap_denoise(y, O.phi_sum(Phi), A, At, iter_max=4, tv_weight=0.1, tv_iter_max=5, X_orig=cube)
+    xg, _, _, pag = scipnp.gap_denoise_cassi(y, m2, nband, step, iter_max=4, tv_weight=0.1, tv_iter_max=5,
+                                             X_orig=cube)
+    Wc = 256 + (nband - 1) * step
+    with Solver(1, 256, Wc, nband, method="gap", tv_weight=0.1, tv_iter_max=5) as so:
+        so.load_cassi(y[None], m2, step)
+        l0 = so.launches
+        ms = _time_run(torch, so.run, ITERS)
+        lpi = (so.launches - l0) / (6. * ITERS)
+        path = "fused" if so.uses_fused else "exact"
+    # the mask is the 2-D aperture read at offsets: x in/out (2NC) + y, y1 in, y1 out, Phi_sum (4N) + aperture
+    entry("c4", "GAP-TV CASSI 256x256x28 bands, 2 px/band (canvas 256x310), aperture read at band offsets", ms,
+          4 * 256 * Wc * (2 * nband + 4) + 4 * 256 * 256, lpi, par(xg, xo, pag, pao, 4), path)
+    return out
+
+
 # -- our arm -----------------------------------------------------------------------------------
 
 def run_ours(args):
@@ -283,6 +397,24 @@ def run_ours(args):
     fused = bool(solver.uses_fused)
     refined = int(solver.refined_iters)
 
+    # -- N > 1: every rank checks the rows it owns against a single-GPU solve of the whole scene --------
+    tiled_parity = None
+    if world > 1:
+        ref = Solver(1, H, W, CR, method="gap", accelerate=True, _lambda=1.0, tv_weight=TV_WEIGHT, tv_iter_max=TV_ITER)
+        yf, Pf, _ = device_scene(torch, H, W, CR)
+        ref.load(yf[None], Pf)
+        ref.run(iters)
+        xr = torch.empty((1, H, W, CR), dtype=torch.float32, device="cuda")
+        ref.get_x(out=xr)
+        d = (solver.owned() - xr[0, solver.lo:solver.hi]).abs().max().reshape(1).double()
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        tiled_parity = {"max_abs_vs_single_gpu": float(d[0]), "iterations": iters, "rows_checked": H,
+                        "what": "owned rows of every rank after the last timed step vs one Solver on the "
+                                "whole 3840x2160x24 scene on the same GPU", "tolerance": "<= 1e-6"}
+        ref.close()
+        del ref, yf, Pf, xr
+        torch.cuda.empty_cache()
+
     # -- end to end through the host-buffer C ABI (N = 1) or the tiled host path ----------------
     e2e = None
     if world == 1:
@@ -341,6 +473,7 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()              # rank 0 is timing the CPU baseline: leave together
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
@@ -349,7 +482,8 @@ def run_ours(args):
     cpu_val, cpu_wall = (None, None)
     cpu = None
     parity = None
-    if world == 1 and not args.no_cpu:
+    configs = None
+    if not args.no_cpu:
         rows, cit = 192, 12
         cpu_val, cpu_wall = cpu_baseline(rows, cit, 1)
         cpu = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
@@ -357,6 +491,12 @@ def run_ours(args):
                          "(reference algorithm, oracle port; NumPy elementwise is single-threaded); "
                          "value scaled to the full scene by rows" % (rows, W, CR, cit, cpu_wall)}
         parity = parity_on_band(cit)
+        if tiled_parity is not None:
+            parity["tiled"] = tiled_parity
+        if world == 1:
+            configs = measure_configs(torch, peak)
+    elif tiled_parity is not None:
+        parity = {"tiled": tiled_parity}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -376,6 +516,7 @@ def run_ours(args):
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu,
         "parity": parity,
+        "configs": configs,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": sampler.summary() if sampler else None,
@@ -386,6 +527,8 @@ def run_ours(args):
             line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    if world > 1:
+        dist.barrier()
     emit(line)
     if world > 1:
         dist.destroy_process_group()

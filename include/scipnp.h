@@ -94,6 +94,20 @@ int scipnp_tv_chambolle(const float *in, float *out, double weight, double eps,
                         int *n_exec_dev, double *energy_dev, int energy_cap,
                         void *stream);
 
+/* R6, one pass over HBM: the same denoiser with all n_iter_max - 1 effective dual updates fused
+ *     into a single launch (n_iter_max 3..5, C % 4 == 0, C <= 24, W % 4 == 0; the intermediates
+ *     live in registers and TMA-staged shared-memory tiles).  The kernel cannot wait
+ *     for skimage's global energy criterion; it evaluates it on the side and sets *flag_dev
+ *     (int, device, caller zeroes it; may be NULL) when some slice would have stopped early --
+ *     the caller then repeats the call with scipnp_tv_chambolle.  Within 1e-6 of it otherwise.
+ *     scipnp_tv_fused_supported: 1 when the shape is covered.                                  */
+size_t scipnp_tv_fused_workspace_bytes(int B, int H, int W, int C, int n_iter_max);
+int scipnp_tv_fused_supported(int B, int H, int W, int C, int n_iter_max);
+int scipnp_tv_chambolle_fused(const float *in, float *out, double weight, double eps,
+                              int n_iter_max, int B, int H, int W, int C,
+                              void *workspace, size_t workspace_bytes, int *flag_dev,
+                              void *stream);
+
 /* MATLAB twin's default TV denoiser (PnP_SCI/matlab/algorithms/tvdenoisers/TV_denoising.m:1-44,
  *     the 'ATV_ClipA' branch of gapdenoise.m:93-94): anisotropic TV by iterative clipping,
  *     alpha = 5, per 2-D frame of a [B][H][W][C] stack; `iters` iterations, the x of the last one

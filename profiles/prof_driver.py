@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: a few outer GAP-TV iterations on the config-5
 scene (3840x2160x24) so the profiler sees the kernels of the timed path only.
-Usage: python profiles/prof_driver.py [iters] [H] [W] [C]"""
+Usage: python profiles/prof_driver.py [iters] [H] [W] [C] [B] [gap|admm]"""
 import os
 import sys
 
@@ -15,14 +15,16 @@ iters = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 2160
 W = int(sys.argv[3]) if len(sys.argv) > 3 else 3840
 C = int(sys.argv[4]) if len(sys.argv) > 4 else 24
+B = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+method = sys.argv[6] if len(sys.argv) > 6 else "gap"
 fused = int(os.environ.get("SCIPNP_FUSED", "1"))
 g = torch.Generator(device="cuda").manual_seed(1)
-Phi = (torch.rand((H, W, C), device="cuda", generator=g) <= 0.5).float()
-orig = torch.rand((H, W, C), device="cuda", generator=g)
-y = (Phi * orig).sum(2)
+Phi = (torch.rand((B, H, W, C), device="cuda", generator=g) <= 0.5).float()
+orig = torch.rand((B, H, W, C), device="cuda", generator=g)
+y = (Phi * orig).sum(3)
 tv_eps = float(os.environ.get("TV_EPS", "2e-4"))      # TV_EPS=0: timing experiments whose results are not meaningful
-s = Solver(1, H, W, C, method="gap", tv_weight=0.3, tv_iter_max=5, fused=bool(fused), tv_eps=tv_eps)
-s.load(y[None], Phi)
+s = Solver(B, H, W, C, method=method, tv_weight=0.3, tv_iter_max=5, fused=bool(fused), tv_eps=tv_eps, phi_batched=B > 1)
+s.load(y, Phi if B > 1 else Phi[0])
 s.run(iters)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,4 +32,4 @@ e0.record()
 s.run(iters)
 e1.record()
 torch.cuda.synchronize()
-print("path=%s  %.3f ms / outer iteration" % ("fused" if s.uses_fused else "exact", e0.elapsed_time(e1) / iters))
+print("%dx%dx%dx%d %s path=%s  %.4f ms / outer iteration" % (B, H, W, C, method, "fused" if s.uses_fused else "exact", e0.elapsed_time(e1) / iters))

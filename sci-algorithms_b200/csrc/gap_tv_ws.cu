@@ -95,7 +95,7 @@ int fused_variant() {
 
 bool fused_ws_supported(const FusedArgs& a) {
     if (fused_variant() == 1) return false;
-    if (a.mode != MODE_GAP_ACC && a.mode != MODE_GAP_PLAIN) return false;
+    if (a.mode != MODE_GAP_ACC && a.mode != MODE_GAP_PLAIN && a.mode != MODE_TV) return false;
     if (a.mask2d) return false;                                   // CASSI index-offset masks: stream kernel
     if (a.clip01) return false;
     const int Q = a.C / 2;
@@ -107,7 +107,9 @@ bool fused_ws_supported(const FusedArgs& a) {
     if (a.tv_iter_max < 3 || a.tv_iter_max > 5) return false;
     if (a.W % 4 != 0 || a.H < 1 || a.B < 1) return false;         // TMA row pitch of the planes; atomic pixel pairs
     if ((long long)a.B * a.H >= (1LL << 31)) return false;
-    if (!aligned16(a.x_in) || !aligned16(a.x_out) || !aligned16(a.Phi) || !aligned16(a.y) || !aligned16(a.Phi_sum)) return false;
+    if (!a.x_in || !a.x_out || a.x_in == a.x_out || !aligned16(a.x_in) || !aligned16(a.x_out)) return false;
+    if (a.mode == MODE_TV) return true;
+    if (!aligned16(a.Phi) || !aligned16(a.y) || !aligned16(a.Phi_sum)) return false;
     if (a.mode == MODE_GAP_ACC && (!a.y1_in || !a.y1_out || !aligned16(a.y1_in))) return false;
     return true;
 }
@@ -154,6 +156,9 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
     const long long ctas = grid;
     MapKey key{a.x_in, a.x_out, a.Phi, a.y, a.mode == MODE_GAP_ACC ? a.y1_in : nullptr, a.Phi_sum,
                a.B, a.H, a.W, a.C, own, p.phi_batched};
+    if (a.mode == MODE_TV) {          // the denoiser alone stages its input only; the other descriptors are never used
+        key.phi = a.x_in; key.y = a.x_in; key.ps = a.x_in; key.phi_batched = 1;
+    }
     alignas(64) WsMaps maps;
     if (int e = get_maps(key, &maps)) return e;
     if (!(a.workspace_clean && a.flag && R > 1))
@@ -215,6 +220,42 @@ void fused_ws_forget(const void* base) {
 }  // namespace scipnp
 
 extern "C" {
+
+size_t scipnp_tv_fused_workspace_bytes(int B, int H, int W, int C, int n_iter_max) {
+    if (B < 1 || H < 1 || W < 1 || C < 1 || n_iter_max < 1) return 0;
+    return scipnp::fused_workspace_bytes(B, H, W, C, n_iter_max);
+}
+
+int scipnp_tv_fused_supported(int B, int H, int W, int C, int n_iter_max) {
+    scipnp::FusedArgs a{};
+    a.mode = scipnp::MODE_TV;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.tv_iter_max = n_iter_max;
+    a.x_in = reinterpret_cast<const float*>(16); a.x_out = reinterpret_cast<float*>(32);      // alignment probes only
+    return scipnp::fused_ws_supported(a) ? 1 : 0;
+}
+
+int scipnp_tv_chambolle_fused(const float* in, float* out, double weight, double eps, int n_iter_max, int B, int H,
+                              int W, int C, void* workspace, size_t workspace_bytes, int* flag_dev, void* stream) {
+    using namespace scipnp;
+    SCIPNP_REQUIRE(B >= 1 && H >= 1 && W >= 1 && C >= 1 && B <= 65535, "bad dimensions");
+    SCIPNP_REQUIRE(in && out && workspace, "null pointer");
+    SCIPNP_REQUIRE(in != out, "in and out must not alias");
+    SCIPNP_REQUIRE(weight > 0.0, "weight must be positive");
+    FusedArgs a{};
+    a.mode = MODE_TV;
+    a.x_in = in; a.x_out = out;
+    a.tv_weight = weight; a.tv_eps = eps; a.tv_iter_max = n_iter_max;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.phi_batched = 1;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    a.flag = flag_dev;
+    if (!fused_ws_supported(a)) {
+        set_error("one-pass TV: needs C %% 4 == 0, C <= 24, W %% 4 == 0, n_iter_max 3..5, 16-byte aligned arrays "
+                  "(use scipnp_tv_chambolle)");
+        return SCIPNP_EINVAL;
+    }
+    SCIPNP_REQUIRE(workspace_bytes >= fused_workspace_bytes(B, H, W, C, n_iter_max), "workspace too small");
+    return launch_fused_ws(a, (cudaStream_t)stream);
+}
 
 // 0: automatic (warp-specialised kernel where it applies), 1: stream kernel only, 2: same as 0
 int scipnp_set_fused_variant(int v) {

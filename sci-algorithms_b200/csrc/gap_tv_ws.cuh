@@ -32,6 +32,18 @@ namespace wsk {
 
 using namespace fusedk;     // PTX helpers, P2 arithmetic
 
+// build-time knobs (tools/build_exp.sh)
+#ifndef WS_RCP
+#define WS_RCP 0          // 0: one MUFU.RCP per value, 1: one per pixel pair, 2: one per four values
+#endif
+#ifndef WS_CREGS
+#define WS_CREGS 0        // > 0: setmaxnreg -- consumers WS_CREGS registers, producers WS_PREGS (12*C + 4*P <= 2048)
+#define WS_PREGS 0
+#endif
+#ifndef WS_EXP
+#define WS_EXP 0          // timing experiments (bit flags; results are meaningless): 1 independent stages, 2 no out-tile
+#endif                    // stores, 4 no energies, 8 no shuffles
+
 constexpr int WRB = 4;            // rows per staged block
 constexpr int GW = 64;            // pixels per group tile (lane = 2 pixels)
 constexpr int HALO = 4;           // halo pixels per side of a group (2 lanes)
@@ -155,9 +167,6 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
     constexpr bool FAST = PATH != 0;          // no row masks
     constexpr bool PXM = PATH != 1;           // pixel masks
     P2 o_new[2] = {f_new[0], f_new[1]};
-#ifndef WS_EXP
-#define WS_EXP 0          // timing experiments (bit flags; results are meaningless): 1 independent stages, 2 no out-tile
-#endif                    // stores, 4 no energies, 8 no shuffles
     P2 o_last[2] = {f_new[0], f_new[1]};
     P2 pi0[2], pi1[2];
     const P2 z = splat(0.f);
@@ -189,9 +198,27 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
             if (!FAST) g0[q] = mul2(g0[q], md2);
             nrm[q] = sqrt2(fma2(g0[q], g0[q], mul2(g1[q], g1[q])));
         }
+        // r = 1 / (1 + (tau/w)|g|) for the four values.  The XU pipe (MUFU: 4 lanes per clock and scheduler) is one of
+        // the kernel's three co-limiters, so the reciprocals of pixel A and pixel B share one MUFU.RCP:
+        // 1/a = b * (1/(ab)), 1/b = a * (1/(ab)).  The denominators are >= 1; ab stays finite up to 1.8e19 each.
         P2 r[2];
-        r[0] = rcp2(fma2(nrm[0], c.tvc2, c.one2));
-        r[1] = rcp2(fma2(nrm[1], c.tvc2, c.one2));
+        {
+            const P2 den0 = fma2(nrm[0], c.tvc2, c.one2), den1 = fma2(nrm[1], c.tvc2, c.one2);
+#if WS_RCP == 1
+            const P2 rc = rcp2(mul2(den0, den1));
+            r[0] = mul2(rc, den1);
+            r[1] = mul2(rc, den0);
+#elif WS_RCP == 2
+            const P2 m = mul2(den0, den1);
+            const float rc = fast_rcp(m.x * m.y);
+            const P2 rx = make_float2(rc * m.y, rc * m.x);
+            r[0] = mul2(rx, den1);
+            r[1] = mul2(rx, den0);
+#else
+            r[0] = rcp2(den0);
+            r[1] = rcp2(den1);
+#endif
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             if (PXM) r[q] = mul2(r[q], m2);
@@ -287,7 +314,7 @@ struct WsSegIter {
     }
 };
 
-// MODE: MODE_GAP_ACC or MODE_GAP_PLAIN.  Q = C/2 channel pairs.
+// MODE: MODE_GAP_ACC, MODE_GAP_PLAIN or MODE_TV (the denoiser alone: f = x_in).  Q = C/2 channel pairs.
 template <int R, int MODE, int Q>
 __global__ void __launch_bounds__(ws_threads(Q), 1)
 gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
@@ -319,8 +346,12 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
     // Every role walks the same sequence of (segment, block) pairs; `gb` counts the blocks of all segments so far and
     // gives the ring slot and the mbarrier phase.
 
+    // Register reallocation between the roles (warpgroups of four warps): the producers give registers back, the
+    // consumers -- whose pipeline state fills the 128 registers a 512-thread CTA starts with -- take them.
+    constexpr bool kRealloc = WS_CREGS > 0 && CW % 4 == 0 && ws_threads(Q) == 512;
     if (warp < CW) {
         // =================================== consumers ===================================
+        if (kRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_CREGS > 0 ? WS_CREGS : 128));
         const int gi = warp / Q, q = warp - gi * Q;
         // f tile: [WRB][NGRP][Q][GW][2] floats; this lane reads 16 bytes (A.c0 A.c1 B.c0 B.c1)
         const uint32_t f_lane = smem_base + L.f_off + ((gi * Q + q) * GW + 2 * lane) * 8;
@@ -434,10 +465,13 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
         }
     } else {
         // =================================== producers ===================================
+        if (kRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(WS_PREGS > 0 ? WS_PREGS : 128));
         const int ptid = tid - CW * 32;                          // 0 .. NPROD*32-1
         constexpr int NPT = NPROD * 32;
         constexpr int NITEM = WRB * NGRP * GW;                   // (row, group, pixel) items per block
-        constexpr uint32_t kTx = 2u * L.x_bytes + (MODE == MODE_GAP_ACC ? 3u : 2u) * NGRP * WRB * GW * 4;
+        constexpr bool TVONLY = MODE == MODE_TV;                 // standalone denoiser: f is the input itself
+        constexpr uint32_t kTx = TVONLY ? (uint32_t)L.x_bytes
+                                        : 2u * L.x_bytes + (MODE == MODE_GAP_ACC ? 3u : 2u) * NGRP * WRB * GW * 4;
         // TMA loads of block `blk` of the segment `sg` into raw slot `g % NRAW` (g = global block index)
         auto issue = [&](const WsSegIter<R>& sg, int blk, int g) {
             const int slot = g % NRAW;
@@ -450,6 +484,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             for (int g2 = 0; g2 < NGRP; ++g2) {
                 const int px0 = (sg.strip * NGRP + g2) * own - HALO;
                 tma_load_3d(dst + g2 * (WRB * GW * C * 4), &maps.x, 0, px0, rowc, bar);
+                if (TVONLY) continue;
                 tma_load_3d(dst + L.x_bytes + g2 * (WRB * GW * C * 4), &maps.phi, 0, px0, prow, bar);
                 const uint32_t ds = dst + L.small_off + g2 * (WRB * GW * 4);
                 tma_load_2d(ds, &maps.y, px0, rowc, bar);
@@ -548,6 +583,18 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 const int gpx = (group0 + g) * own - HALO + px;
                 const bool in = (group0 + g) < p.ngroups && gpx >= 0 && gpx < W && row < H;
                 const float4* tx = reinterpret_cast<const float4*>(raw) + ((g * WRB + j) * GW + px) * K;
+                // f tile: [WRB][NGRP][Q][GW][2]
+                float2* frow = reinterpret_cast<float2*>(fdst) + ((j * NGRP + g) * Q) * GW + px;
+                if constexpr (TVONLY) {
+#pragma unroll
+                    for (int k0 = 0; k0 < K; ++k0) {
+                        const int kc = k0 ^ lsw;
+                        const float4 v = tx[kc];                     // pixels outside the image: zero-filled by TMA
+                        frow[(2 * kc) * GW] = make_float2(v.x, v.y);
+                        frow[(2 * kc + 1) * GW] = make_float2(v.z, v.w);
+                    }
+                    continue;
+                }
                 const float4* tp = tx + L.x_bytes / 16;
                 float4 xv[K], pv[K];
 #pragma unroll
@@ -571,8 +618,6 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     sv = (yv - acc) * fast_rcp(psv);
                 }
                 const P2 s2 = splat(in ? sv * lam : 0.f);
-                // f tile: [WRB][NGRP][Q][GW][2]
-                float2* frow = reinterpret_cast<float2*>(fdst) + ((j * NGRP + g) * Q) * GW + px;
 #pragma unroll
                 for (int k0 = 0; k0 < K; ++k0) {
                     const int kc = k0 ^ lsw;
@@ -670,6 +715,7 @@ int ws_launch_mode(int Q, const WsParams& p, const WsMaps& maps, int grid, cudaS
 #define SCIPNP_INSTANTIATE_WS_R(RR)                                                                              \
     template <> int ws_launch_r<RR>(int mode, int Q, const WsParams& p, const WsMaps& maps, int grid, cudaStream_t st) { \
         if (mode == MODE_GAP_ACC) return ws_launch_mode<RR, MODE_GAP_ACC>(Q, p, maps, grid, st);                 \
+        if (mode == MODE_TV) return ws_launch_mode<RR, MODE_TV>(Q, p, maps, grid, st);                           \
         return ws_launch_mode<RR, MODE_GAP_PLAIN>(Q, p, maps, grid, st);                                         \
     }
 

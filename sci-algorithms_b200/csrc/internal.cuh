@@ -4,7 +4,7 @@
 
 namespace scipnp {
 
-enum { MODE_GAP_ACC = 0, MODE_GAP_PLAIN = 1, MODE_ADMM = 2 };
+enum { MODE_GAP_ACC = 0, MODE_GAP_PLAIN = 1, MODE_ADMM = 2, MODE_TV = 3 };   // MODE_TV: warp-specialised kernel only
 
 // ops.cu
 int launch_project(int mode, const float* a_in, const float* b_in, float* x_out, float* f_out,

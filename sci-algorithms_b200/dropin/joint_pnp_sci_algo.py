@@ -3,6 +3,6 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from scipnp.joint_pnp_sci_algo import (admm_denoise, gap_denoise, gap_multistep_denoise,     # noqa: F401,E402
+from scipnp.joint_pnp_sci_algo import (joint_admmdenoise_cacti, admm_denoise, gap_denoise, gap_multistep_denoise,     # noqa: F401,E402
                                        gap_joint_denoise, admm_multistep_denoise, admm_joint_denoise,
                                        A_, At_, psnr)

@@ -1,6 +1,7 @@
 """Drop-in for the TV paths of the reference's ``PnP_SCI/python/joint_pnp_sci_algo.py``
 (SURVEY.md section 8f-1): the module most ``pnp_sci_test_*`` drivers import.
 
+    joint_admmdenoise_cacti  :20-79  coded-frame loop around the two-period drivers below
     admm_denoise   joint_pnp_sci_algo.py:502-665   ADMM-TV with ``theta = clip(theta, 0, 1)`` (:633)
     gap_denoise    joint_pnp_sci_algo.py:666-...    same loop as pnp_sci_algo.gap_denoise
 
@@ -24,8 +25,54 @@ from .iqa import frames_iqa
 from .tiled import _wrap
 from .utils import A_, At_, psnr  # noqa: F401
 
-__all__ = ["admm_denoise", "gap_denoise", "gap_multistep_denoise", "gap_joint_denoise",
+__all__ = ["joint_admmdenoise_cacti", "admm_denoise", "gap_denoise", "gap_multistep_denoise", "gap_joint_denoise",
            "admm_multistep_denoise", "admm_joint_denoise", "A_", "At_", "psnr"]
+
+
+def joint_admmdenoise_cacti(meas, mask, A=None, At=None, projmeth='admm', v0=None, orig=None,
+                            iframe=0, nframe=1, MAXB=1., maskdirection='plain', denoiser='tv',
+                            iter_max1=50, iter_max2=50, sigma1=None, sigma2=None, **args):
+    """Coded-frame loop of the joint module (joint_pnp_sci_algo.py:20-79): every coded frame runs the
+    two-period driver (``admm_joint_denoise`` / ``gap_joint_denoise``); ``v0`` and the results are
+    reversed along the frame axis for the down-going masks of 'updown' / 'downup'.  The mask is handed
+    to the solvers as ``Phi=`` (the wrapper knows it; ``A``/``At`` may stay ``None``).  Returns
+    ``(x_, t_, psnr_, ssim_, psnrall_)``."""
+    import time
+    pm = str(projmeth).lower()
+    if pm not in ('admm', 'gap'):
+        raise ValueError('Unsupported projection method %s' % str(projmeth).upper())
+    mask = f32c(_host(mask))
+    meas = _host(meas)
+    nrow, ncol, nmask = mask.shape
+    x_ = np.zeros((nrow, ncol, nmask * nframe), dtype=np.float32)
+    psnr_, ssim_, psnrall_ = [], [], []
+    t0 = time.time()
+    mask_sum = np.sum(mask, axis=2)
+    mask_sum[mask_sum == 0] = 1
+    md = str(maskdirection).lower()
+    args.setdefault('Phi', mask)
+    t_ = 0.
+    for kf in range(nframe):
+        orig_k = None if orig is None else _host(orig)[:, :, (kf + iframe) * nmask:(kf + iframe + 1) * nmask] / MAXB
+        meas_k = meas[:, :, kf + iframe] / MAXB
+        down = (md == 'updown' and (kf + iframe) % 2 == 1) or (md == 'downup' and (kf + iframe) % 2 == 0)
+        v0_k = None
+        if v0 is not None:
+            v0_k = _host(v0)[:, :, kf * nmask:(kf + 1) * nmask]
+            if down:
+                v0_k = v0_k[:, :, ::-1]
+        joint = admm_joint_denoise if pm == 'admm' else gap_joint_denoise
+        x_k, psnr_k, ssim_k, psnrall_k = joint(meas_k, mask_sum, A, At, x0=v0_k, X_orig=orig_k, denoiser=denoiser,
+                                               iter_max1=iter_max1, iter_max2=iter_max2, sigma1=sigma1,
+                                               sigma2=sigma2, **args)
+        if down:
+            x_k, psnr_k, ssim_k, psnrall_k = x_k[:, :, ::-1], psnr_k[::-1], ssim_k[::-1], psnrall_k[::-1]
+        t_ = time.time() - t0
+        x_[:, :, kf * nmask:(kf + 1) * nmask] = x_k
+        psnr_.extend(psnr_k)
+        ssim_.extend(ssim_k)
+        psnrall_.append(psnrall_k)
+    return x_, t_, psnr_, ssim_, psnrall_
 
 
 def admm_denoise(y, Phi_sum, A=None, At=None, _lambda=1, gamma=0.0, accelerate=None,

@@ -307,6 +307,17 @@ def denoise_tv_chambolle(image, weight=0.1, eps=2.e-4, n_iter_max=200, multichan
         H, W = d.shape
         Cc = 1
     out = torch.empty_like(d)
+    if USE_FUSED and multichannel and not return_stats and lib.scipnp_tv_fused_supported(1, H, W, Cc, int(n_iter_max)) \
+            and d.data_ptr() % 16 == 0:
+        # one pass over HBM (all dual updates in one launch); the exact kernels below take over when the
+        # energy criterion of skimage would have stopped a slice early
+        fwb = lib.scipnp_tv_fused_workspace_bytes(1, H, W, Cc, int(n_iter_max))
+        fws = torch.empty(fwb, dtype=torch.uint8, device=d.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=d.device)
+        check(lib.scipnp_tv_chambolle_fused(dptr(d), dptr(out), float(weight), float(eps), int(n_iter_max),
+                                            1, H, W, Cc, dptr(fws), fwb, dptr(flag), stream_ptr()))
+        if int(flag.item()) == 0:
+            return out if is_torch(src) else out.cpu().numpy()
     wsb = lib.scipnp_tv_workspace_bytes(1, H, W, Cc)
     ws = torch.empty(wsb, dtype=torch.uint8, device=d.device)
     n_exec = energy = None

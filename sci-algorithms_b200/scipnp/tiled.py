@@ -92,11 +92,14 @@ class TiledSolver:
     """One rank of the row-tiled GAP-TV solver (accelerated GAP, TV prior)."""
 
     def __init__(self, H, W, C, rank, world, tv_weight=0.1, tv_iter_max=5, _lambda=1.0,
-                 accelerate=True, exchange_every=1, group=None, fused=True, transport="nccl"):
+                 accelerate=True, exchange_every=1, group=None, fused=True, transport="nccl",
+                 tv_eps=2.e-4, method="gap"):
         """transport: "nccl" (send/recv pairs through torch.distributed), "p2p" (CUDA-IPC
         mapped neighbour buffers, halo rows pulled over NVLink by the library, device-side
         flags) or "auto" (p2p when every rank can set it up, else nccl)."""
         from .engine import Solver
+        if str(method).lower() != "gap":
+            raise NotImplementedError("the row-tiled mode runs GAP-TV (ADMM-TV scenes are sharded per measurement)")
         self.H, self.W, self.C = H, W, C
         self.rank, self.world, self.group = rank, world, group
         self.k = max(1, int(exchange_every))
@@ -106,7 +109,7 @@ class TiledSolver:
         self.accelerate = accelerate
         self.solver = Solver(1, self.local_rows, W, C, method="gap", accelerate=accelerate,
                              _lambda=_lambda, tv_weight=tv_weight, tv_iter_max=tv_iter_max,
-                             fused=fused)
+                             tv_eps=tv_eps, fused=fused)
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.exchanges = 0
         self.transport = "nccl"
@@ -220,6 +223,10 @@ class TiledSolver:
             out.copy_(res)
             return out
         return res.clone()
+
+    def result(self):
+        """Owned rows of the current estimate (a copy; the solver's buffers ping-pong)."""
+        return self.owned()
 
     @property
     def uses_fused(self):

@@ -155,3 +155,66 @@ def test_ws_kernel_early_stop_flag(sp, variant):
         s.run(2)
         xe = s.get_x()
     np.testing.assert_array_equal(xg, xe)
+
+
+# -- the denoiser alone (north_star subsystem 2): MODE_TV of the same kernel ------------------------
+
+@pytest.mark.parametrize("H,W,C,T", [(64, 128, 8, 5), (37, 60, 24, 5), (50, 52, 4, 3), (9, 300, 12, 4), (130, 64, 16, 5)])
+def test_fused_tv_alone_matches_oracle(sp, H, W, C, T):
+    """scipnp_tv_chambolle_fused (all dual updates in one launch) against the oracle's skimage restatement,
+    through the C ABI; eps = 0 keeps the stopping rule out of both."""
+    import torch
+    from scipnp._lib import lib, check
+    from scipnp.engine import dptr, stream_ptr
+    from oracle.tv_chambolle import denoise_tv_chambolle as tv_oracle
+    assert lib.scipnp_tv_fused_supported(1, H, W, C, T) == 1
+    rng = np.random.default_rng(H * W + C)
+    img = (0.5 + 0.25 * rng.standard_normal((H, W, C))).astype(np.float32)
+    ref = tv_oracle(img, 0.3, eps=0.0, n_iter_max=T, multichannel=True)
+    d = torch.from_numpy(img).cuda()
+    out = torch.empty_like(d)
+    wsb = lib.scipnp_tv_fused_workspace_bytes(1, H, W, C, T)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.scipnp_tv_chambolle_fused(dptr(d), dptr(out), 0.3, 0.0, T, 1, H, W, C, dptr(ws), wsb, dptr(flag), stream_ptr()))
+    assert int(flag.item()) == 0
+    assert float(np.abs(out.cpu().numpy() - ref).max()) <= 2e-6
+
+
+def test_fused_tv_alone_batched_through_the_abi(sp):
+    """B > 1: every (b, c) slice is its own problem; rows of neighbouring batch elements never mix."""
+    import torch
+    from scipnp._lib import lib, check
+    from scipnp.engine import dptr, stream_ptr
+    from oracle.tv_chambolle import denoise_tv_chambolle as tv_oracle
+    B, H, W, C, T = 3, 21, 64, 8, 5
+    rng = np.random.default_rng(5)
+    img = rng.random((B, H, W, C)).astype(np.float32)
+    d = torch.from_numpy(img).cuda()
+    out = torch.empty_like(d)
+    wsb = lib.scipnp_tv_fused_workspace_bytes(B, H, W, C, T)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    check(lib.scipnp_tv_chambolle_fused(dptr(d), dptr(out), 0.2, 0.0, T, B, H, W, C, dptr(ws), wsb, None, stream_ptr()))
+    got = out.cpu().numpy()
+    for b in range(B):
+        assert float(np.abs(got[b] - tv_oracle(img[b], 0.2, eps=0.0, n_iter_max=T, multichannel=True)).max()) <= 2e-6
+
+
+def test_denoise_tv_chambolle_uses_the_one_pass_kernel_and_keeps_the_early_stop(sp):
+    """The public R6 entry: one launch when the rule does not fire, the exact kernels (and skimage's
+    result) when it does."""
+    from scipnp._lib import lib
+    from oracle.tv_chambolle import denoise_tv_chambolle as tv_oracle
+    rng = np.random.default_rng(11)
+    img = rng.random((48, 64, 8)).astype(np.float32)
+    l0 = lib.scipnp_launch_count()
+    got = sp.denoise_tv_chambolle(img, 0.3, n_iter_max=5, multichannel=True)
+    assert lib.scipnp_launch_count() - l0 == 1
+    assert float(np.abs(got - tv_oracle(img, 0.3, n_iter_max=5, multichannel=True)).max()) <= 2e-6
+    # a nearly flat image with a large eps: the rule fires at the first check
+    flat = (0.5 + 1e-3 * rng.random((48, 64, 8))).astype(np.float32)
+    l0 = lib.scipnp_launch_count()
+    got = sp.denoise_tv_chambolle(flat, 0.3, eps=0.5, n_iter_max=5, multichannel=True)
+    assert lib.scipnp_launch_count() - l0 > 1
+    np.testing.assert_array_equal(got, tv_oracle(flat, 0.3, eps=0.5, n_iter_max=5, multichannel=True))
+    assert lib.scipnp_tv_fused_supported(1, 48, 64, 8, 30) == 0 and lib.scipnp_tv_fused_supported(1, 48, 63, 8, 5) == 0
