@@ -469,7 +469,7 @@ def run_ours(args):
                                "api": "scipnp_gap_denoise_host (one synchronous call)"}}
         assert float(xh.abs().sum()) > 0
     else:
-        e2e = solver.e2e_measure(y, Phi, iters, min(args.steps, 3))
+        e2e = solver.e2e_measure(y, Phi, iters, args.steps)
 
     if rank != 0:
         if world > 1:
@@ -521,10 +521,19 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": sampler.summary() if sampler else None,
     }
+    # dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture -- only while the capture
+    # was taken on the kernel sources of this tree (tools/capture_traffic.py stamps their hash)
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(traffic_file):
         try:
-            line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from capture_traffic import source_hash
+            rec = json.load(open(traffic_file))
+            if rec.get("source_hash") == source_hash():
+                line["roofline"]["traffic"] = rec.get("dram_bytes_per_launch")
+                line["roofline"]["traffic_source"] = "profiles/traffic.json (%s, sources %s)" % (rec.get("report"), rec.get("source_hash"))
+            else:
+                line["roofline"]["traffic_source"] = "profiles/traffic.json is stale (taken on other kernel sources): null"
         except Exception:
             pass
     if world > 1:

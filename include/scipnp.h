@@ -277,6 +277,15 @@ int scipnp_solver_ipc_attach(scipnp_solver *s, int side, const unsigned char *bl
 int scipnp_solver_exchange(scipnp_solver *s, void *stream);
 int scipnp_solver_run_tiled(scipnp_solver *s, int iters, int k, void *stream);
 int scipnp_solver_sync_error(scipnp_solver *s, int *timed_out, void *stream);
+/* skimage's stopping rule of the TV step (pnp_sci_algo.py:650 -> denoise_tv_chambolle) compares energies summed
+ * over the WHOLE image.  On the exact path a tiled handle sums its owned rows only and hands the 2*C partial
+ * energies of every dual iteration (device doubles) to `reduce`, which must sum them over all ranks in place,
+ * ordered on `stream` (e.g. an NCCL all-reduce); `total_rows` is the height of the whole scene.  With it the
+ * exact path of the tiled mode takes the stopping decisions of the single-GPU solve.  The one-pass kernel keeps
+ * its per-tile side check (rows of the tile): it only decides whether the run is redone on the exact path.    */
+typedef int (*scipnp_energy_reduce_fn)(double *partials_dev, int n, void *stream, void *user);
+int scipnp_solver_set_energy_reduce(scipnp_solver *s, scipnp_energy_reduce_fn reduce, void *user,
+                                    long long total_rows);
 
 /* Host-buffer one-call entries (what a ctypes / cffi binding of the reference
  * would call in place of gap_denoise / admm_denoise).  Synchronous.  psnr_all

@@ -48,7 +48,8 @@ constexpr int WRB = 4;            // rows per staged block
 constexpr int GW = 64;            // pixels per group tile (lane = 2 pixels)
 constexpr int HALO = 4;           // halo pixels per side of a group (2 lanes)
 constexpr int OWN_MAX = GW - 2 * HALO;
-constexpr int NPROD = 4;          // producer warps
+constexpr int NPROD = 4;          // producer-side warps: one TMA warp (loader lane + storer lane) and NCOMP projection warps
+constexpr int NCOMP = NPROD - 1;
 constexpr int NRAW = 2;           // ring depth of the raw (TMA-staged) tiles
 constexpr int NOUT = 2;           // ring depth of the output tiles
 
@@ -109,7 +110,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(NPROD * 32) : "memory"); }
 
 // non-blocking poll (test_wait returns at once; try_wait may suspend the thread for a system-dependent time)
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
@@ -148,7 +148,7 @@ struct WsPipe {
     P2 g1b[R];           // horizontal difference of out_i(u) at the right pixel (its neighbour is a SHFL)
     P2 P0[R][2];         // p^{i+1}(u-1), vertical component
     P2 P1[R][2];         //               horizontal component
-    P2 fd[R][2];         // fd[j] = f(t-1-j)
+    P2 fd[R - 1][2];     // fd[j] = f(t-1-j), j < R-1; the last stage's f(t-R) is read back from the f ring
     P2 en[R];            // energy partials of dual iterations 0..R-1 (both pixels)
 };
 
@@ -158,12 +158,15 @@ struct WsConst {
     int rs, r0, r1, H;
 };
 
-// One pipeline step: f_new = f(t) enters, out_R(t-R) is returned in o_out.
+// One pipeline step: f_new = f(t) enters, out_R(t-R) is returned in o_out.  f_old = f(t-R) closes the last stage
+// (out_R = f + D p^R); it comes from shared memory, so that the register delay line holds R-1 rows: together with
+// f(t) that is R = WRB live rows, a period the unrolled block of WRB rows maps onto fixed registers without moves.
 // PATH 1 (fast): every row touched lies inside [r0, r1) and the image and the whole group lies inside the image.
 // PATH 2 (edge): the rows as in 1, but the group hangs over the left or right image edge: pixel masks only.
 // PATH 0 (general): row masks and pixel masks.
 template <int R, int PATH>
-__device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, const P2 (&f_new)[2], P2 (&o_out)[2]) {
+__device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, const P2 (&f_new)[2], const P2 (&f_old)[2],
+                                        P2 (&o_out)[2]) {
     constexpr bool FAST = PATH != 0;          // no row masks
     constexpr bool PXM = PATH != 1;           // pixel masks
     P2 o_new[2] = {f_new[0], f_new[1]};
@@ -257,7 +260,7 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
         S.g1b[i] = g1b_new;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            const P2 o_next = add2(S.fd[i][q], d[q]);
+            const P2 o_next = add2(i == R - 1 ? f_old[q] : S.fd[i < R - 1 ? i : 0][q], d[q]);
             // the dual variable stage i+1 needs now is the one this stage produced in the previous step
             pi0[q] = S.P0[i][q];
             pi1[q] = S.P1[i][q];
@@ -270,7 +273,7 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
     }
     if (FAST && (WS_EXP & 1)) { o_new[0] = o_last[0]; o_new[1] = o_last[1]; }
 #pragma unroll
-    for (int i = R - 1; i > 0; --i) { S.fd[i][0] = S.fd[i - 1][0]; S.fd[i][1] = S.fd[i - 1][1]; }
+    for (int i = R - 2; i > 0; --i) { S.fd[i][0] = S.fd[i - 1][0]; S.fd[i][1] = S.fd[i - 1][1]; }
     S.fd[0][0] = f_new[0];
     S.fd[0][1] = f_new[1];
     o_out[0] = o_new[0];
@@ -327,15 +330,16 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    // mbarriers: raw_full[NRAW], f_full[NF], f_empty[NF], out_full[NOUT], out_empty[NOUT]
+    // mbarriers: raw_full[NRAW], raw_empty[NRAW], f_full[NF], f_empty[NF], out_full[NOUT], out_empty[NOUT]
     const uint32_t bar_raw = smem_base + L.bar_off;
-    const uint32_t bar_ffull = bar_raw + 8 * NRAW;
+    const uint32_t bar_rempty = bar_raw + 8 * NRAW;
+    const uint32_t bar_ffull = bar_rempty + 8 * NRAW;
     const uint32_t bar_fempty = bar_ffull + 8 * NF;
     const uint32_t bar_ofull = bar_fempty + 8 * NF;
     const uint32_t bar_oempty = bar_ofull + 8 * NOUT;
     if (tid == 0) {
-        for (int i = 0; i < NRAW; ++i) mbar_init(bar_raw + 8 * i, 1);
-        for (int i = 0; i < NF; ++i) { mbar_init(bar_ffull + 8 * i, NPROD); mbar_init(bar_fempty + 8 * i, CW); }
+        for (int i = 0; i < NRAW; ++i) { mbar_init(bar_raw + 8 * i, 1); mbar_init(bar_rempty + 8 * i, NCOMP); }
+        for (int i = 0; i < NF; ++i) { mbar_init(bar_ffull + 8 * i, NCOMP); mbar_init(bar_fempty + 8 * i, CW); }
         for (int i = 0; i < NOUT; ++i) { mbar_init(bar_ofull + 8 * i, CW); mbar_init(bar_oempty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         fence_async_smem();
@@ -384,7 +388,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
         for (int i = 0; i < R; ++i) {
             S.g1b[i] = z; S.en[i] = z;
 #pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2) { S.o_prev[i][k2] = z; S.P0[i][k2] = z; S.P1[i][k2] = z; S.fd[i][k2] = z; }
+            for (int k2 = 0; k2 < 2; ++k2) { S.o_prev[i][k2] = z; S.P0[i][k2] = z; S.P1[i][k2] = z; if (i < R - 1) S.fd[i][k2] = z; }
         }
         sc.pair_in = pair_in ? 1.f : 0.f;
         sc.right_in = (pair_in && pxa + 2 < W) ? 1.f : 0.f;
@@ -400,7 +404,11 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             mbar_wait(bar_oempty + 8 * os, ((gb / NOUT) & 1) ^ 1);
             if (p.prof) pw1 += clock64() - c1;
             const uint32_t fsrc = f_lane + fs * L.f_bytes;
+            const uint32_t fprev = f_lane + ((gb + NF - 1) % NF) * L.f_bytes;      // the previous block's rows (kept until this block is done)
             const uint32_t odst = o_lane + os * L.out_bytes;
+            static_assert(R <= WRB, "f(t-R) must lie in this block or the previous one");
+            // shared-memory address of f(t0 + j - R)
+            auto f_old_addr = [&](int j) { return j >= R ? fsrc + (j - R) * F_ROW : fprev + (j - R + WRB) * F_ROW; };
             const int t0 = rs + blk * WRB;
             const bool rows_fast = t0 >= fast_lo && t0 + WRB - 1 <= fast_hi;
             auto fast_block = [&](auto path) {
@@ -410,8 +418,11 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     float4 fv;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(fv.x), "=f"(fv.y), "=f"(fv.z), "=f"(fv.w) : "r"(fsrc + j * F_ROW));
                     const P2 f_new[2] = {make_float2(fv.x, fv.y), make_float2(fv.z, fv.w)};
+                    float4 fo;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(fo.x), "=f"(fo.y), "=f"(fo.z), "=f"(fo.w) : "r"(f_old_addr(j)));
+                    const P2 f_old[2] = {make_float2(fo.x, fo.y), make_float2(fo.z, fo.w)};
                     P2 o[2];
-                    ws_step<R, PATH>(S, sc, t0 + j, f_new, o);
+                    ws_step<R, PATH>(S, sc, t0 + j, f_new, f_old, o);
                     if (own_lane && (!(WS_EXP & 2) || o[0].x == 123.456f)) {
                         asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW), "f"(o[0].x), "f"(o[0].y) : "memory");
                         asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW + 16), "f"(o[1].x), "f"(o[1].y) : "memory");
@@ -430,8 +441,12 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                         float4 fv;
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(fv.x), "=f"(fv.y), "=f"(fv.z), "=f"(fv.w) : "r"(fsrc + j * F_ROW));
                         const P2 f_new[2] = {make_float2(fv.x, fv.y), make_float2(fv.z, fv.w)};
+                        float4 fo = make_float4(0.f, 0.f, 0.f, 0.f);          // rows above the segment: never used unmasked
+                        if (t - R >= rs)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(fo.x), "=f"(fo.y), "=f"(fo.z), "=f"(fo.w) : "r"(f_old_addr(j)));
+                        const P2 f_old[2] = {make_float2(fo.x, fo.y), make_float2(fo.z, fo.w)};
                         P2 o[2];
-                        ws_step<R, 0>(S, sc, t, f_new, o);
+                        ws_step<R, 0>(S, sc, t, f_new, f_old, o);
                         if (own_lane) {
                             asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW), "f"(o[0].x), "f"(o[0].y) : "memory");
                             asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW + 16), "f"(o[1].x), "f"(o[1].y) : "memory");
@@ -443,7 +458,10 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(bar_ofull + 8 * os);
-                mbar_arrive(bar_fempty + 8 * fs);
+                // the last stage reads f(t-R) out of the previous block's slot: a slot is handed back one block late,
+                // the last one of a segment together with its predecessor
+                if (blk > 0) mbar_arrive(bar_fempty + 8 * ((gb + NF - 1) % NF));
+                if (blk == nblk - 1) mbar_arrive(bar_fempty + 8 * fs);
             }
         }
         // energy partials of this segment: owned lanes only, one atomic per (channel, iteration)
@@ -466,83 +484,72 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
     } else {
         // =================================== producers ===================================
         if (kRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(WS_PREGS > 0 ? WS_PREGS : 128));
-        const int ptid = tid - CW * 32;                          // 0 .. NPROD*32-1
-        constexpr int NPT = NPROD * 32;
+        constexpr int NPT = NCOMP * 32;
         constexpr int NITEM = WRB * NGRP * GW;                   // (row, group, pixel) items per block
         constexpr bool TVONLY = MODE == MODE_TV;                 // standalone denoiser: f is the input itself
         constexpr uint32_t kTx = TVONLY ? (uint32_t)L.x_bytes
                                         : 2u * L.x_bytes + (MODE == MODE_GAP_ACC ? 3u : 2u) * NGRP * WRB * GW * 4;
-        // TMA loads of block `blk` of the segment `sg` into raw slot `g % NRAW` (g = global block index)
-        auto issue = [&](const WsSegIter<R>& sg, int blk, int g) {
-            const int slot = g % NRAW;
-            const uint32_t dst = smem_base + slot * L.raw_bytes;
-            const uint32_t bar = bar_raw + 8 * slot;
-            const int row0 = sg.rs + blk * WRB;
-            const int rowc = sg.b * H + row0, prow = (p.phi_batched ? sg.b * H : 0) + row0;
-            mbar_expect_tx(bar, kTx);
+        if (warp == CW) {
+            // ------------- the TMA warp: lane 0 loads, lane 1 stores, each walking the block sequence on its own.
+            // Neither ever waits for the other, and the projection warps never wait for a store: a finished output
+            // block leaves for HBM as soon as the last consumer warp has arrived.
+            if (lane == 0) {
+                WsSegIter<R> ld(p);
+                int g = 0;
+#pragma unroll 1
+                while (ld.next()) {
+#pragma unroll 1
+                    for (int blk = 0; blk < ld.nblk; ++blk, ++g) {
+                        const int slot = g % NRAW;
+                        mbar_wait(bar_rempty + 8 * slot, ((g / NRAW) & 1) ^ 1);      // the projection warps are done with it
+                        const uint32_t dst = smem_base + slot * L.raw_bytes;
+                        const uint32_t bar = bar_raw + 8 * slot;
+                        const int row0 = ld.rs + blk * WRB;
+                        const int rowc = ld.b * H + row0, prow = (p.phi_batched ? ld.b * H : 0) + row0;
+                        mbar_expect_tx(bar, kTx);
 #pragma unroll
-            for (int g2 = 0; g2 < NGRP; ++g2) {
-                const int px0 = (sg.strip * NGRP + g2) * own - HALO;
-                tma_load_3d(dst + g2 * (WRB * GW * C * 4), &maps.x, 0, px0, rowc, bar);
-                if (TVONLY) continue;
-                tma_load_3d(dst + L.x_bytes + g2 * (WRB * GW * C * 4), &maps.phi, 0, px0, prow, bar);
-                const uint32_t ds = dst + L.small_off + g2 * (WRB * GW * 4);
-                tma_load_2d(ds, &maps.y, px0, rowc, bar);
-                if (MODE == MODE_GAP_ACC) tma_load_2d(ds + NGRP * WRB * GW * 4, &maps.y1, px0, rowc, bar);
-                tma_load_2d(ds + 2 * NGRP * WRB * GW * 4, &maps.ps, px0, prow, bar);
-            }
-        };
-        // The loader (thread 0 of the producers) runs NRAW blocks ahead of the producers, across segment boundaries
-        WsSegIter<R> ld(p);
-        bool ld_live = ld.next();
-        int ld_blk = 0, ld_g = 0;
-        auto load_next = [&]() {                                  // thread ptid == 0 only
-            if (!ld_live) return;
-            issue(ld, ld_blk, ld_g);
-            ++ld_g;
-            if (++ld_blk == ld.nblk) { ld_blk = 0; ld_live = ld.next(); }
-        };
-        // The first producer warp is also the storer: whenever every consumer warp has finished the rows of an
-        // output block, its lane 0 hands the owned pixels of the rows inside [r0, r1) to the TMA unit.  It polls
-        // while it waits for the consumers (never blocks on the output ring), so the rings cannot deadlock.
-        const bool storer = warp == CW;
-        WsSegIter<R> st(p);
-        bool st_live = st.next();
-        int st_blk = 0, st_g = 0;
-        auto store_block = [&]() {                                // lane 0 of the storer warp
-            const int os = st_g % NOUT;
-            const uint32_t src = smem_base + L.out_off + os * L.out_bytes;
-            for (int j = 0; j < WRB; ++j) {
-                const int orow = st.rs + st_blk * WRB + j - R;
-                if (orow >= st.r0 && orow < st.r1) {
-                    for (int g2 = 0; g2 < NGRP; ++g2)
-                        if (st.strip * NGRP + g2 < p.ngroups)
-                            tma_store_4d(&maps.out, src + (j * NGRP + g2) * L.out_sub, 0, (st.strip * NGRP + g2) * own, 0, st.b * H + orow);
+                        for (int g2 = 0; g2 < NGRP; ++g2) {
+                            const int px0 = (ld.strip * NGRP + g2) * own - HALO;
+                            tma_load_3d(dst + g2 * (WRB * GW * C * 4), &maps.x, 0, px0, rowc, bar);
+                            if (TVONLY) continue;
+                            tma_load_3d(dst + L.x_bytes + g2 * (WRB * GW * C * 4), &maps.phi, 0, px0, prow, bar);
+                            const uint32_t ds = dst + L.small_off + g2 * (WRB * GW * 4);
+                            tma_load_2d(ds, &maps.y, px0, rowc, bar);
+                            if (MODE == MODE_GAP_ACC) tma_load_2d(ds + NGRP * WRB * GW * 4, &maps.y1, px0, rowc, bar);
+                            tma_load_2d(ds + 2 * NGRP * WRB * GW * 4, &maps.ps, px0, prow, bar);
+                        }
+                    }
                 }
-            }
-            bulk_commit();
-            bulk_wait_read0();
-            mbar_arrive(bar_oempty + 8 * os);
-        };
-        auto store_advance = [&]() {                              // whole storer warp
-            ++st_g;
-            if (++st_blk == st.nblk) { st_blk = 0; st_live = st.next(); }
-        };
-        auto store_poll = [&]() {
-            if (st_live) {
-                int ready = 0;
-                if (lane == 0) ready = mbar_try(bar_ofull + 8 * (st_g % NOUT), (st_g / NOUT) & 1) ? 1 : 0;
-                ready = __shfl_sync(0xffffffffu, ready, 0);
-                if (ready) {
-                    if (lane == 0) store_block();
-                    __syncwarp();
-                    store_advance();
+            } else if (lane == 1) {
+                WsSegIter<R> st(p);
+                int g = 0;
+#pragma unroll 1
+                while (st.next()) {
+#pragma unroll 1
+                    for (int blk = 0; blk < st.nblk; ++blk, ++g) {
+                        const int os = g % NOUT;
+                        mbar_wait(bar_ofull + 8 * os, (g / NOUT) & 1);
+                        const uint32_t src = smem_base + L.out_off + os * L.out_bytes;
+                        for (int j = 0; j < WRB; ++j) {
+                            const int orow = st.rs + blk * WRB + j - R;
+                            if (orow >= st.r0 && orow < st.r1) {
+                                for (int g2 = 0; g2 < NGRP; ++g2)
+                                    if (st.strip * NGRP + g2 < p.ngroups)
+                                        tma_store_4d(&maps.out, src + (j * NGRP + g2) * L.out_sub, 0, (st.strip * NGRP + g2) * own, 0, st.b * H + orow);
+                            }
+                        }
+                        bulk_commit();
+                        bulk_wait_read0();
+                        mbar_arrive(bar_oempty + 8 * os);
+                    }
                 }
+                bulk_wait0();
             }
-        };
+        } else {
+        // ------------- projection warps
+        const int ptid = tid - (CW + 1) * 32;                    // 0 .. NCOMP*32-1
         long long pw0 = 0, pw1 = 0, pw2 = 0;
         const long long pstart = p.prof ? clock64() : 0;
-        if (ptid == 0) { load_next(); load_next(); }
         const float lam = p.lambda;
         // bank pattern of the lane-per-pixel 16-byte reads: pixels are C*4 bytes apart.  For K = 2, 6 every
         // other group of four lanes visits the chunk pairs in swapped order, for K = 4 the chunk index is
@@ -562,17 +569,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             if (p.prof) c0 = clock64();
             mbar_wait(bar_raw + 8 * slot, (gb / NRAW) & 1);
             if (p.prof) { c1 = clock64(); pw0 += c1 - c0; }
-            if (storer) {
-                store_poll();
-                for (;;) {
-                    int ok = 0;
-                    if (lane == 0) ok = mbar_try_sleep(bar_fempty + 8 * fs, ((gb / NF) & 1) ^ 1, 256) ? 1 : 0;
-                    if (__shfl_sync(0xffffffffu, ok, 0)) break;
-                    store_poll();
-                }
-            } else {
-                mbar_wait(bar_fempty + 8 * fs, ((gb / NF) & 1) ^ 1);
-            }
+            mbar_wait(bar_fempty + 8 * fs, ((gb / NF) & 1) ^ 1);
             if (p.prof) pw1 += clock64() - c1;
             const unsigned char* raw = smem_raw + slot * L.raw_bytes;
             unsigned char* fdst = smem_raw + L.f_off + fs * L.f_bytes;
@@ -626,26 +623,17 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_ffull + 8 * fs);
-            if (p.prof) c0 = clock64();
-            prod_bar();                              // every producer is done reading the raw slot
-            if (p.prof) pw2 += clock64() - c0;
-            if (ptid == 0) load_next();
+            if (lane == 0) {
+                mbar_arrive(bar_ffull + 8 * fs);
+                mbar_arrive(bar_rempty + 8 * slot);          // this warp is done reading the raw slot
+            }
         }
         }   // segments
         if (p.prof && lane == 0) {
             long long* pr = p.prof + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * 4;
             pr[0] = clock64() - pstart; pr[1] = pw0; pr[2] = pw1; pr[3] = pw2;
         }
-        if (storer) {
-            while (st_live) {
-                mbar_wait(bar_ofull + 8 * (st_g % NOUT), (st_g / NOUT) & 1);
-                if (lane == 0) store_block();
-                __syncwarp();
-                store_advance();
-            }
-            if (lane == 0) bulk_wait0();
-        }
+        }   // projection warps
     }
 
     // ---- skimage's stopping rule, replayed by the last CTA on the accumulated energies

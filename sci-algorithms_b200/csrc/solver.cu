@@ -65,6 +65,7 @@ struct scipnp_solver {
     int* sync = nullptr;                      // [0] ready<-up [1] ready<-down [2] ack<-up [3] ack<-down [4] timeout
     int epoch = 0;
     bool ack_pending = false;
+    TvTiling tv_tiling;                       // owned rows + cross-rank energy sum for the exact path's stopping rule
     PeerLink up, dn;
 
     float* x_cur() { return xa; }
@@ -235,7 +236,8 @@ static int step_exact(scipnp_solver* s, int k, cudaStream_t st) {
         if (int e = launch_project(mode, s->xa, nullptr, s->xa, nullptr, s->y1a, s->y1a, s->y, s->Phi,
                                    s->PhiSum, p.lambda, 0.f, p.B, p.H, p.W, p.C, p.phi_batched, st)) return e;
         if (int e = tv_chambolle_exact(s->xa, s->xb, p.tv_weight, p.tv_eps, p.tv_iter_max, p.B, p.H, p.W,
-                                       p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st)) return e;
+                                       p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st,
+                                       s->tiled && s->tv_tiling.reduce ? &s->tv_tiling : nullptr)) return e;
         std::swap(s->xa, s->xb);
         if (p.clip01) if (int e = launch_clip01(s->xa, s->n_frame, st)) return e;
         if (int e = record_sqerr(s, k, s->xa, st)) return e;
@@ -555,6 +557,18 @@ int scipnp_solver_tiling(scipnp_solver* s, int lo, int hi, int row_lo, int row_h
     s->tiled = true;
     s->epoch = 0;
     s->ack_pending = false;
+    s->tv_tiling.e_lo = lo - row_lo;
+    s->tv_tiling.e_hi = hi - row_lo;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_set_energy_reduce(scipnp_solver* s, scipnp_energy_reduce_fn reduce, void* user, long long total_rows) {
+    SCIPNP_REQUIRE(s, "null solver");
+    if (!s->tiled) { set_error("call scipnp_solver_tiling first"); return SCIPNP_ESTATE; }
+    SCIPNP_REQUIRE(total_rows >= s->p.H, "total_rows is smaller than this tile");
+    s->tv_tiling.reduce = reduce;
+    s->tv_tiling.user = user;
+    s->tv_tiling.total_rows = total_rows;
     return SCIPNP_OK;
 }
 

@@ -87,6 +87,7 @@ _SIGS = {
     "scipnp_solver_tiling": (C.c_int, [_vp, _i, _i, _i, _i]),
     "scipnp_solver_ipc_export": (C.c_int, [_vp, C.c_char_p]),
     "scipnp_solver_ipc_attach": (C.c_int, [_vp, _i, C.c_char_p, _i]),
+    "scipnp_solver_set_energy_reduce": (C.c_int, [_vp, _vp, _vp, C.c_longlong]),
     "scipnp_solver_exchange": (C.c_int, [_vp, _vp]),
     "scipnp_solver_run_tiled": (C.c_int, [_vp, _i, _i, _vp]),
     "scipnp_solver_sync_error": (C.c_int, [_vp, C.POINTER(_i), _vp]),

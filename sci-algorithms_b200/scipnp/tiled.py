@@ -79,13 +79,13 @@ def exchange_halos(fields, H, halo, rank, world, group=None):
 class _DevView:
     """Expose a raw device pointer to torch through __cuda_array_interface__."""
 
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4",
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
                                          "data": (int(ptr), False), "version": 3, "strides": None}
 
 
-def _wrap(ptr, shape, device):
-    return torch.as_tensor(_DevView(ptr, shape), device=device)
+def _wrap(ptr, shape, device, typestr="<f4"):
+    return torch.as_tensor(_DevView(ptr, shape, typestr), device=device)
 
 
 class TiledSolver:
@@ -113,8 +113,28 @@ class TiledSolver:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.exchanges = 0
         self.transport = "nccl"
+        if world > 1:
+            self._setup_energy_reduce()
         if transport in ("p2p", "auto") and world > 1:
             self._setup_p2p(required=(transport == "p2p"))
+
+    def _setup_energy_reduce(self):
+        """skimage's stopping rule sums energies over the whole image: on the exact path the library hands the
+        per-slice partial sums over this rank's owned rows to this callback, which all-reduces them in place
+        (stream-ordered with NCCL; through the host with gloo)."""
+        import ctypes as ct
+        from ._lib import lib, check
+        check(lib.scipnp_solver_tiling(self.solver._h, self.lo, self.hi, self.row_lo, self.row_hi))
+
+        def reduce(dev_ptr, n, stream, user):
+            try:
+                t = _wrap(dev_ptr, (n,), self.device, "<f8")
+                dist.all_reduce(t, group=self.group)
+                return 0
+            except Exception:       # noqa: BLE001  (must not propagate through the C frame)
+                return 1
+        self._reduce_cb = ct.CFUNCTYPE(ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_void_p)(reduce)
+        check(lib.scipnp_solver_set_energy_reduce(self.solver._h, ct.cast(self._reduce_cb, ct.c_void_p), None, self.H))
 
     def _setup_p2p(self, required):
         """Map the neighbours' solver buffers (CUDA IPC) so that halo rows are pulled straight
@@ -239,39 +259,89 @@ class TiledSolver:
     def close(self):
         self.solver.close()
 
+    # -- host-buffer path: a stream of reconstructions, copies under the kernels -------------------------
+    def run_host_stream(self, jobs, iters):
+        """Reconstruct a sequence of scenes whose row blocks live in pinned host memory.  ``jobs`` is a list of
+        ``(y_host, Phi_host, out_host)`` (this rank's rows [row_lo, row_hi) of y and Phi, its owned rows of the
+        result), all pinned.  The H2D copy of job i+1 and the D2H copy of job i-1 run on a copy stream under the
+        iterations of job i (two device staging sets, two result buffers); nothing is allocated per job.
+        Returns when every result has landed in its ``out_host``."""
+        dev = self.device
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [(torch.empty((self.local_rows, self.W), dtype=torch.float32, device=dev),
+                            torch.empty((self.local_rows, self.W, self.C), dtype=torch.float32, device=dev))
+                           for _ in range(2)]
+            self._res = [torch.empty((self.hi - self.lo, self.W, self.C), dtype=torch.float32, device=dev)
+                         for _ in range(2)]
+        cs = self._copy_stream
+        up = [None, None]          # event: staging set i holds its job
+        taken = [None, None]       # event: the solver has copied staging set i into its own buffers
+        solved = [None, None]      # event: result buffer i holds a finished job
+        drained = [None, None]     # event: result buffer i has left for the host
+
+        def upload(i):
+            k = i % 2
+            with torch.cuda.stream(cs):
+                if taken[k] is not None:
+                    cs.wait_event(taken[k])
+                self._stage[k][0].copy_(jobs[i][0], non_blocking=True)
+                self._stage[k][1].copy_(jobs[i][1], non_blocking=True)
+                up[k] = cs.record_event()
+
+        if jobs:
+            upload(0)
+        for i in range(len(jobs)):
+            k = i % 2
+            if i + 1 < len(jobs):
+                upload(i + 1)
+            main.wait_event(up[k])
+            self.load(self._stage[k][0], self._stage[k][1])
+            taken[k] = main.record_event()
+            self.run(iters)
+            if drained[k] is not None:
+                main.wait_event(drained[k])
+            self.owned(out=self._res[k])
+            solved[k] = main.record_event()
+            with torch.cuda.stream(cs):
+                cs.wait_event(solved[k])
+                jobs[i][2].copy_(self._res[k], non_blocking=True)
+                drained[k] = cs.record_event()
+        cs.synchronize()
+        main.synchronize()
+
     # -- end-to-end measurement used by bench.py -------------------------------------------
     def e2e_measure(self, y_local, Phi_local, iters, steps):
-        """Host-buffer path at N GPUs: pinned host inputs -> device -> solve -> owned rows back."""
+        """Host-buffer path at N GPUs: every step copies this rank's rows of y and Phi up from pinned host memory
+        and its owned rows of the result down; the copies of neighbouring steps overlap the iterations
+        (``run_host_stream``)."""
         import time
         yh = y_local.cpu().pin_memory()
         Ph = Phi_local.cpu().pin_memory()
-        out = torch.empty((self.hi - self.lo, self.W, self.C), dtype=torch.float32).pin_memory()
-
-        def step():
-            self.load(yh.cuda(non_blocking=True), Ph.cuda(non_blocking=True))
-            self.run(iters)
-            out.copy_(self.owned(), non_blocking=True)
-            torch.cuda.synchronize()
-        step()
+        outs = [torch.empty((self.hi - self.lo, self.W, self.C), dtype=torch.float32).pin_memory() for _ in range(2)]
+        steps = max(1, steps)
+        self.run_host_stream([(yh, Ph, outs[0])], iters)                     # warm-up (allocates the staging sets)
         if self.world > 1:
             dist.barrier(self.group)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(max(1, steps)):
-            step()
+        self.run_host_stream([(yh, Ph, outs[i % 2]) for i in range(steps)], iters)
         if self.world > 1:
             dist.barrier(self.group)
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if self.world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX, group=self.group)
         h2d = torch.tensor([yh.numel() * 4 + Ph.numel() * 4], dtype=torch.float64, device="cuda")
-        d2h = torch.tensor([out.numel() * 4], dtype=torch.float64, device="cuda")
+        d2h = torch.tensor([outs[0].numel() * 4], dtype=torch.float64, device="cuda")
         if self.world > 1:
             dist.all_reduce(h2d, group=self.group)
             dist.all_reduce(d2h, group=self.group)
-        return {"value": max(1, steps) * iters / float(dt[0]), "unit": "it/s",
-                "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]),
-                "steps": max(1, steps), "api": "scipnp.tiled.TiledSolver (pinned host buffers per rank)"}
+        assert float(outs[(steps - 1) % 2].abs().sum()) > 0
+        return {"value": steps * iters / float(dt[0]), "unit": "it/s",
+                "h2d_bytes_per_step": int(h2d[0]), "d2h_bytes_per_step": int(d2h[0]), "steps": steps,
+                "api": "scipnp.tiled.TiledSolver.run_host_stream (pinned host buffers per rank, copies on a second "
+                       "stream under the iterations of the neighbouring steps)"}
 
 
 def tiled_reference_run(step_fn, fields, H, halo, k, iters, rank, world, group=None):

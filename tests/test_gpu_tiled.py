@@ -26,7 +26,7 @@ def sp():
     return scipnp
 
 
-def _worker(rank, world, port, H, W, C, iters, k, fused, tv_eps, method, out_dir):
+def _worker(rank, world, port, H, W, C, iters, k, fused, tv_eps, method, out_dir, T=5):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -38,7 +38,7 @@ def _worker(rank, world, port, H, W, C, iters, k, fused, tv_eps, method, out_dir
         from scipnp import synth
         meas, mask, _ = synth.make_cacti(H, W, C, 1, cfg=21)
         y = meas[:, :, 0] / np.float32(255.)
-        ts = TiledSolver(H, W, C, rank, world, tv_weight=0.3, tv_iter_max=5, exchange_every=k, transport="p2p",
+        ts = TiledSolver(H, W, C, rank, world, tv_weight=0.3, tv_iter_max=T, exchange_every=k, transport="p2p",
                          fused=fused, tv_eps=tv_eps, method=method)
         assert ts.transport == "p2p", "fell back to %s" % ts.transport
         ts.load(torch.from_numpy(y[ts.row_lo:ts.row_hi]).cuda(), torch.from_numpy(mask[ts.row_lo:ts.row_hi]).cuda())
@@ -51,21 +51,21 @@ def _worker(rank, world, port, H, W, C, iters, k, fused, tv_eps, method, out_dir
         dist.destroy_process_group()
 
 
-def _tiled(tmp_path, world, H, W, C, iters, k, fused=True, tv_eps=2e-4, method="gap"):
+def _tiled(tmp_path, world, H, W, C, iters, k, fused=True, tv_eps=2e-4, method="gap", T=5):
     import socket
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(world, port, H, W, C, iters, k, fused, tv_eps, method, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, H, W, C, iters, k, fused, tv_eps, method, str(tmp_path), T), nprocs=world, join=True)
     got = np.concatenate([np.load(tmp_path / ("x_%d.npy" % r)) for r in range(world)], axis=0)
     meta = np.stack([np.load(tmp_path / ("meta_%d.npy" % r)) for r in range(world)])
     return got, meta
 
 
-def _single(H, W, C, iters, fused=True, tv_eps=2e-4, method="gap"):
+def _single(H, W, C, iters, fused=True, tv_eps=2e-4, method="gap", T=5):
     from scipnp import synth, Solver
     meas, mask, _ = synth.make_cacti(H, W, C, 1, cfg=21)
     y = meas[:, :, 0] / np.float32(255.)
-    with Solver(1, H, W, C, method=method, tv_weight=0.3, tv_iter_max=5, fused=fused, tv_eps=tv_eps) as so:
+    with Solver(1, H, W, C, method=method, tv_weight=0.3, tv_iter_max=T, fused=fused, tv_eps=tv_eps) as so:
         so.load(y[None], mask)
         so.run(iters // 2)
         so.run(iters - iters // 2)
@@ -109,4 +109,62 @@ def test_p2p_tiled_config5_width(sp, tmp_path):
     got, meta = _tiled(tmp_path, 2, H, W, C, iters, 2)
     ref, _ = _single(H, W, C, iters)
     assert (meta[:, 1] == 1).all()
+    assert float(np.abs(got - ref).max()) <= 1e-6
+
+
+def _stream_worker(rank, world, port, H, W, C, iters, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from scipnp.tiled import TiledSolver
+        from scipnp import synth
+        ts = TiledSolver(H, W, C, rank, world, tv_weight=0.3, tv_iter_max=5, exchange_every=2, transport="p2p")
+        jobs = []
+        for j in range(3):
+            meas, mask, _ = synth.make_cacti(H, W, C, 1, cfg=70 + j)
+            y = meas[:, :, 0] / np.float32(255.)
+            jobs.append((torch.from_numpy(np.ascontiguousarray(y[ts.row_lo:ts.row_hi])).pin_memory(),
+                         torch.from_numpy(np.ascontiguousarray(mask[ts.row_lo:ts.row_hi])).pin_memory(),
+                         torch.empty((ts.hi - ts.lo, W, C), dtype=torch.float32).pin_memory()))
+        ts.run_host_stream(jobs, iters)
+        for j in range(3):
+            np.save(os.path.join(out_dir, "s_%d_%d.npy" % (j, rank)), jobs[j][2].numpy())
+        ts.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_host_stream_of_reconstructions(sp, tmp_path):
+    """run_host_stream: three different scenes from pinned host buffers, copies overlapped with the iterations
+    of the neighbouring jobs (two staging sets): every job equals the single-GPU solve of its scene."""
+    import socket
+    import torch.multiprocessing as mp
+    from scipnp import synth, Solver
+    world, H, W, C, iters = 2, 136, 128, 8, 5
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_stream_worker, args=(world, port, H, W, C, iters, str(tmp_path)), nprocs=world, join=True)
+    for j in range(3):
+        meas, mask, _ = synth.make_cacti(H, W, C, 1, cfg=70 + j)
+        y = meas[:, :, 0] / np.float32(255.)
+        with Solver(1, H, W, C, method="gap", tv_weight=0.3, tv_iter_max=5) as so:
+            so.load(y[None], mask)
+            so.run(iters)
+            ref = so.get_x()[0]
+        got = np.concatenate([np.load(tmp_path / ("s_%d_%d.npy" % (j, r))) for r in range(world)], axis=0)
+        assert float(np.abs(got - ref).max()) <= 1e-6, "job %d" % j
+
+
+def test_p2p_tiled_stopping_rule_sums_energies_over_all_ranks(sp, tmp_path):
+    """tv_iter_max = 20 with an eps at which slices stop at different dual iterations: the exact path all-reduces the
+    per-slice energies of the owned rows (scipnp_solver_set_energy_reduce), so every tile stops where the
+    single-GPU solve stops.  The same scene with eps = 0 differs visibly, i.e. the rule did fire."""
+    H, W, C, iters = 160, 128, 8, 3
+    got, meta = _tiled(tmp_path, 2, H, W, C, iters, 1, fused=False, tv_eps=2e-3, T=20)
+    ref, _ = _single(H, W, C, iters, fused=False, tv_eps=2e-3, T=20)
+    full, _ = _single(H, W, C, iters, fused=False, tv_eps=0.0, T=20)
+    assert float(np.abs(ref - full).max()) > 1e-4, "the stopping rule never fired: the test would be vacuous"
     assert float(np.abs(got - ref).max()) <= 1e-6

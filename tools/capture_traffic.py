@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""profiles/traffic.json from an `ncu --set full` report of the fused kernel, stamped with the hash of the kernel
+sources it was measured on.  bench.py reports roofline.traffic only while that hash equals the hash of the
+sources in the tree (a stale capture reads as null).
+
+    python tools/capture_traffic.py gpurun_out/<report>.ncu-rep [kernel-index]
+"""
+import csv
+import glob
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def source_hash():
+    h = hashlib.sha256()
+    for p in sorted(glob.glob(os.path.join(ROOT, "sci-algorithms_b200", "csrc", "*"))):
+        if p.endswith((".cu", ".cuh")):
+            h.update(os.path.basename(p).encode())
+            h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def main():
+    rep = sys.argv[1]
+    idx = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    d = dict(zip(rows[0], zip(rows[1], rows[2 + idx])))
+
+    def val(k):
+        unit, v = d[k]
+        scale = {"byte": 1., "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.}
+        return float(v.replace(",", "")) * scale.get(unit, 1.)
+    rec = {"kernel": d["Kernel Name"][1][:120], "report": os.path.basename(rep),
+           "dram_bytes_read_per_launch": val("dram__bytes_read.sum"),
+           "dram_bytes_write_per_launch": val("dram__bytes_write.sum"),
+           "gpu_time_s_under_ncu": val("gpu__time_duration.sum"), "source_hash": source_hash(),
+           "note": "one ncu --set full capture of one launch on the 3840x2160x24 scene (profiles/prof_driver.py)"}
+    rec["dram_bytes_per_launch"] = rec["dram_bytes_read_per_launch"] + rec["dram_bytes_write_per_launch"]
+    json.dump(rec, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    print(json.dumps(rec))
+
+
+if __name__ == "__main__":
+    main()
