@@ -127,8 +127,9 @@ def test_tv_properties_large(sp):
     c = torch.full((64, 64, 8), 0.25, device="cuda")
     assert torch.equal(sp.denoise_tv_chambolle(c, 0.3, n_iter_max=5, multichannel=True), c)
     # channels are independent problems
+    # (one channel runs the exact path, 24 channels the one-pass kernel: FMA contraction and MUFU rounding differ)
     one = sp.denoise_tv_chambolle(f[:, :, 3].contiguous(), 0.3, n_iter_max=5)
-    assert torch.equal(one, out[:, :, 3])
+    assert float((one - out[:, :, 3]).abs().max()) <= 1e-5
     # total variation does not increase
     def tv(u):
         return float((u[1:] - u[:-1]).abs().sum() + (u[:, 1:] - u[:, :-1]).abs().sum())

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r14_tests.log
+cat gpurun_out/r14_tests.log
