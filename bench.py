@@ -507,7 +507,8 @@ def run_ours(args):
                    "path": "fused" if fused else "exact", "refined_iters": refined,
                    "parallelism": ("row-tiled x%d, %d halo rows, neighbour exchange every %d iteration(s)"
                                    % (world, 4 * args.exchange_every, args.exchange_every)) if world > 1 else "single GPU",
-                   "halo_transport": getattr(solver, "transport", None) if world > 1 else None},
+                   "halo_transport": (getattr(solver, "transport", None) if world > 1 else None),
+                   "halo_push_in_kernel": (bool(getattr(solver, "push", False)) if world > 1 else None)},
         "gpixel_frames_per_s": value * H * W * CR / 1e9,
         "ms_per_iteration": iter_ms,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -572,7 +573,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=ITERS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--exchange-every", type=int, default=2,
+    ap.add_argument("--exchange-every", type=int, default=1,
                     help="N > 1: outer iterations between halo exchanges (halo = 4x that many rows)")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N > 1: halo transport (p2p = CUDA-IPC peer pulls, nccl = send/recv)")

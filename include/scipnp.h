@@ -283,6 +283,18 @@ int scipnp_solver_sync_error(scipnp_solver *s, int *timed_out, void *stream);
  * ordered on `stream` (e.g. an NCCL all-reduce); `total_rows` is the height of the whole scene.  With it the
  * exact path of the tiled mode takes the stopping decisions of the single-GPU solve.  The one-pass kernel keeps
  * its per-tile side check (rows of the tile): it only decides whether the run is redone on the exact path.    */
+/* Halo push (tiles whose halo is exactly tv_iter_max-1 rows per neighbour, i.e. one exchange per iteration): the
+ * fused kernel produces the owned rows only, stores the rows next to a seam a second time into the neighbour's halo
+ * rows of its output buffers (TMA stores / plain stores over NVLink into the IPC-mapped buffers) and its last CTA
+ * raises the neighbours' flags; the next launch's loader waits for this rank's flags before it touches halo rows.
+ * No exchange kernel, no acknowledgement (nobody reads remote memory).  up_rows / dn_rows = local row counts of the
+ * neighbours.  _run_tiled(k = 1) uses it while the handle is on the fused path; the exact path keeps the pull.
+ * _energy_log: TV energies [iterations since _begin][B*C][tv_iter_max-1] over this rank's owned rows (device
+ * doubles, valid once the stream drained): summed over the ranks they give skimage's stopping rule for the whole
+ * scene (pnp_sci_algo.py:650 -> denoise_tv_chambolle's eps test).                                             */
+int scipnp_solver_enable_push(scipnp_solver *s, int up_rows, int dn_rows);
+int scipnp_solver_uses_push(scipnp_solver *s);
+int scipnp_solver_energy_log(scipnp_solver *s, double **dev, int *iterations, int *per_iteration);
 typedef int (*scipnp_energy_reduce_fn)(double *partials_dev, int n, void *stream, void *user);
 int scipnp_solver_set_energy_reduce(scipnp_solver *s, scipnp_energy_reduce_fn reduce, void *user,
                                     long long total_rows);

@@ -20,9 +20,12 @@ int g_variant = -1;      // -1: from the environment (SCIPNP_FUSED_VARIANT), 0: 
 struct MapKey {
     const float *x_in, *x_out, *phi, *y, *y1, *ps;
     int B, H, W, C, own, phi_batched;
+    const float *x_up = nullptr, *x_dn = nullptr;      // halo push: the neighbours' output buffers and their row counts
+    int up_rows = 0, dn_rows = 0;
     bool operator==(const MapKey& o) const {
         return x_in == o.x_in && x_out == o.x_out && phi == o.phi && y == o.y && y1 == o.y1 && ps == o.ps &&
-               B == o.B && H == o.H && W == o.W && C == o.C && own == o.own && phi_batched == o.phi_batched;
+               B == o.B && H == o.H && W == o.W && C == o.C && own == o.own && phi_batched == o.phi_batched &&
+               x_up == o.x_up && x_dn == o.x_dn && up_rows == o.up_rows && dn_rows == o.dn_rows;
     }
 };
 struct MapEntry { MapKey key; WsMaps maps; bool valid = false; unsigned long long stamp = 0; };
@@ -56,6 +59,10 @@ int build_maps(const MapKey& k, WsMaps* m) {
         unsigned long long str[3] = {(unsigned long long)k.C * 4, 16, (unsigned long long)k.W * k.C * 4};
         unsigned box[4] = {4, (unsigned)k.own, (unsigned)k.C / 4, 1};
         if (int e = make_tensor_map_f32(&m->out, k.x_out, 4, dims, str, box, 0)) return e;
+        m->out_up = m->out;
+        m->out_dn = m->out;
+        if (k.x_up) { dims[3] = (unsigned long long)k.up_rows; if (int e = make_tensor_map_f32(&m->out_up, k.x_up, 4, dims, str, box, 0)) return e; }
+        if (k.x_dn) { dims[3] = (unsigned long long)k.dn_rows; if (int e = make_tensor_map_f32(&m->out_dn, k.x_dn, 4, dims, str, box, 0)) return e; }
     }
     return SCIPNP_OK;
 }
@@ -146,8 +153,12 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
     p.tv_w = (float)a.tv_weight;
     p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C;
     p.phi_batched = a.phi_batched ? 1 : 0;
+    p.out_lo = a.out_hi > 0 ? a.out_lo : 0;
+    p.out_hi = a.out_hi > 0 ? a.out_hi : a.H;
+    if (p.out_lo < 0 || p.out_hi > a.H || p.out_lo >= p.out_hi) { set_error("bad output row window"); return SCIPNP_EINVAL; }
+    p.energy_log = a.energy_log;
     int own = OWN_MAX, grid = 1;
-    ws_split(a.B, a.H, a.W, Q, &own, &grid);
+    ws_split(a.B, p.out_hi - p.out_lo, a.W, Q, &own, &grid);
     if (const char* e = getenv("SCIPNP_WS_OWN")) { int v = atoi(e); if (v >= 4 && v <= OWN_MAX && v % 4 == 0) own = v; }
     if (const char* e = getenv("SCIPNP_WS_GRID")) { int v = atoi(e); if (v >= 1) grid = v; }
     p.own = own;
@@ -158,6 +169,29 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
                a.B, a.H, a.W, a.C, own, p.phi_batched};
     if (a.mode == MODE_TV) {          // the denoiser alone stages its input only; the other descriptors are never used
         key.phi = a.x_in; key.y = a.x_in; key.ps = a.x_in; key.phi_batched = 1;
+    }
+    if (a.push) {
+        const TilePush& t = *a.push;
+        if (a.B != 1 || (!t.x_up && !t.x_dn)) { set_error("halo push: one scene, at least one neighbour"); return SCIPNP_EINVAL; }
+        // the window must leave R halo rows towards every neighbour and the neighbours' halo rows must exist
+        if ((t.x_up && (p.out_lo < R || p.out_lo + t.up_shift < 0 || p.out_lo + R + t.up_shift > t.up_rows)) ||
+            (t.x_dn && (a.H - p.out_hi < R || p.out_hi - R + t.dn_shift < 0 || p.out_hi + t.dn_shift > t.dn_rows)) ||
+            p.out_hi - p.out_lo < R) {
+            set_error("halo push: row window and neighbour geometry do not match");
+            return SCIPNP_EINVAL;
+        }
+        key.x_up = t.x_up; key.x_dn = t.x_dn; key.up_rows = t.up_rows; key.dn_rows = t.dn_rows;
+        p.up_shift = t.up_shift; p.dn_shift = t.dn_shift;
+        // y1 rows: my local (row, px) index + shift rows
+        if (a.mode == MODE_GAP_ACC) {
+            p.y1_up = t.y1_up ? t.y1_up + (long long)t.up_shift * a.W : nullptr;
+            p.y1_dn = t.y1_dn ? t.y1_dn + (long long)t.dn_shift * a.W : nullptr;
+            if ((t.x_up && !t.y1_up) || (t.x_dn && !t.y1_dn)) { set_error("halo push: accelerated GAP needs the neighbours' y1"); return SCIPNP_EINVAL; }
+        }
+        p.wait_up = t.x_up ? t.wait_up : nullptr; p.wait_dn = t.x_dn ? t.wait_dn : nullptr;
+        p.sig_up = t.x_up ? t.sig_up : nullptr; p.sig_dn = t.x_dn ? t.sig_dn : nullptr;
+        p.wait_epoch = t.wait_epoch; p.sig_epoch = t.sig_epoch;
+        p.timeout_flag = t.timeout_flag;
     }
     alignas(64) WsMaps maps;
     if (int e = get_maps(key, &maps)) return e;
@@ -214,7 +248,7 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
 void fused_ws_forget(const void* base) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (auto& e : g_cache)
-        if (e.valid && (e.key.x_in == base || e.key.x_out == base || e.key.phi == base)) e.valid = false;
+        if (e.valid && (e.key.x_in == base || e.key.x_out == base || e.key.phi == base || e.key.x_up == base || e.key.x_dn == base)) e.valid = false;
 }
 
 }  // namespace scipnp

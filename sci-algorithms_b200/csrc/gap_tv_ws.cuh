@@ -66,9 +66,23 @@ struct WsParams {
     int nstrips;                  // ceil(ngroups / NGRP): column strips
     int phi_batched;
     long long* prof;              // optional [grid][warps][4] cycle counters (SCIPNP_WS_PROF), else null
+    // Output row window [out_lo, out_hi) inside the H local rows (the whole scene: [0, H)).  A rank of the row-tiled
+    // multi-GPU mode produces its owned rows only; the rows outside the window are halo rows, input only.
+    int out_lo, out_hi;
+    double* energy_log;           // this launch's [B][C][R] energies are also left here (null: not kept)
+    // ---- halo push (row-tiled mode, one exchange per iteration, no exchange kernel): the R owned rows next to a
+    // seam are stored a second time, into the neighbour's halo rows of ITS output buffers (CUDA-IPC mapped, NVLink);
+    // the last CTA raises the neighbours' flags to sig_epoch; the loader lane waits for my flags to reach wait_epoch
+    // before it touches a block that holds halo rows or the owned rows next to them.
+    float* y1_up; float* y1_dn;   // the neighbours' y1_out, shifted so that my local (row, px) index applies
+    int up_shift, dn_shift;       // my local row + shift = the neighbour's local row (TMA store coordinate)
+    const int* wait_up; const int* wait_dn;
+    int* sig_up; int* sig_dn;
+    int wait_epoch, sig_epoch;
+    int* timeout_flag;
 };
 
-struct WsMaps { CUtensorMap x, phi, y, y1, ps, out; };
+struct WsMaps { CUtensorMap x, phi, y, y1, ps, out, out_up, out_dn; };
 
 // pixel groups per CTA for Q = C/2 channel pairs: about 12 consumer warps
 __host__ __device__ constexpr int ws_groups(int Q) { return 12 / Q < 1 ? 1 : 12 / Q; }
@@ -134,6 +148,25 @@ __device__ __forceinline__ bool mbar_try_sleep(uint32_t bar, uint32_t parity, ui
         "selp.u32 %0, 1, 0, p;\n"
         "}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
     return ok != 0;
+}
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// spin until a neighbour's flag reached `need` (8 s time-out, reported through *timeout), then order the TMA
+// (async proxy) reads that follow behind the acquire
+static __device__ __noinline__ void wait_peer_flag(const int* f, int need, int* timeout) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < need) {
+        __nanosleep(64);
+        if (clock64() - t0 > 16000000000LL) { if (timeout) atomicExch(timeout, 1); break; }
+    }
+    asm volatile("fence.proxy.async;\n" ::: "memory");
 }
 
 __device__ __forceinline__ P2 shfl_dn2(P2 a) {
@@ -287,10 +320,10 @@ constexpr int kWsSegCost = 16;    // cost of starting a row segment, in rows (wa
 template <int R>
 struct WsSegIter {
     long long unit, unit_end;
-    int Hv, H, nstrips;
+    int Hv, H, lo, nstrips;
     int b, strip, r0, r1, rs, t_end, nblk;      // current segment
     __device__ WsSegIter(const WsParams& p, int per_cta_unused = 0) {
-        H = p.H; Hv = p.H + kWsSegCost; nstrips = p.nstrips;
+        H = p.H; lo = p.out_lo; Hv = (p.out_hi - p.out_lo) + kWsSegCost; nstrips = p.nstrips;
         const long long total = (long long)p.B * p.nstrips * Hv;
         const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
         unit = (long long)blockIdx.x * per_cta;
@@ -303,8 +336,8 @@ struct WsSegIter {
             const long long left = unit_end - unit;
             const int v1 = (long long)(Hv - v0) < left ? Hv : v0 + (int)left;
             unit += v1 - v0;
-            r0 = v0 - kWsSegCost > 0 ? v0 - kWsSegCost : 0;
-            r1 = v1 - kWsSegCost;
+            r0 = lo + (v0 - kWsSegCost > 0 ? v0 - kWsSegCost : 0);
+            r1 = lo + v1 - kWsSegCost;
             if (r1 <= r0) continue;                                  // only charge units: no rows here
             b = s / nstrips;
             strip = s - b * nstrips;
@@ -465,7 +498,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             }
         }
         // energy partials of this segment: owned lanes only, one atomic per (channel, iteration)
-        if (p.flag != nullptr) {
+        if (p.flag != nullptr || p.energy_log != nullptr) {
 #pragma unroll
             for (int i = 0; i < R; ++i)
 #pragma unroll
@@ -496,6 +529,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             if (lane == 0) {
                 WsSegIter<R> ld(p);
                 int g = 0;
+                bool up_ok = p.wait_up == nullptr, dn_ok = p.wait_dn == nullptr;
 #pragma unroll 1
                 while (ld.next()) {
 #pragma unroll 1
@@ -505,6 +539,10 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                         const uint32_t dst = smem_base + slot * L.raw_bytes;
                         const uint32_t bar = bar_raw + 8 * slot;
                         const int row0 = ld.rs + blk * WRB;
+                        // Halo rows hold what the neighbour pushed in its previous iteration, and the owned rows next
+                        // to a seam are pushed into buffers the neighbour read in that iteration: both need its flag.
+                        if (!up_ok && row0 < p.out_lo + R) { wait_peer_flag(p.wait_up, p.wait_epoch, p.timeout_flag); up_ok = true; }
+                        if (!dn_ok && row0 + WRB > p.out_hi - R) { wait_peer_flag(p.wait_dn, p.wait_epoch, p.timeout_flag); dn_ok = true; }
                         const int rowc = ld.b * H + row0, prow = (p.phi_batched ? ld.b * H : 0) + row0;
                         mbar_expect_tx(bar, kTx);
 #pragma unroll
@@ -533,9 +571,16 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                         for (int j = 0; j < WRB; ++j) {
                             const int orow = st.rs + blk * WRB + j - R;
                             if (orow >= st.r0 && orow < st.r1) {
+                                const bool to_up = p.sig_up != nullptr && orow < p.out_lo + R;
+                                const bool to_dn = p.sig_dn != nullptr && orow >= p.out_hi - R;
                                 for (int g2 = 0; g2 < NGRP; ++g2)
-                                    if (st.strip * NGRP + g2 < p.ngroups)
-                                        tma_store_4d(&maps.out, src + (j * NGRP + g2) * L.out_sub, 0, (st.strip * NGRP + g2) * own, 0, st.b * H + orow);
+                                    if (st.strip * NGRP + g2 < p.ngroups) {
+                                        const uint32_t sub = src + (j * NGRP + g2) * L.out_sub;
+                                        const int px0 = (st.strip * NGRP + g2) * own;
+                                        tma_store_4d(&maps.out, sub, 0, px0, 0, st.b * H + orow);
+                                        if (to_up) tma_store_4d(&maps.out_up, sub, 0, px0, 0, orow + p.up_shift);
+                                        if (to_dn) tma_store_4d(&maps.out_dn, sub, 0, px0, 0, orow + p.dn_shift);
+                                    }
                             }
                         }
                         bulk_commit();
@@ -544,6 +589,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     }
                 }
                 bulk_wait0();
+                if (p.sig_up != nullptr || p.sig_dn != nullptr) __threadfence_system();     // pushed rows before the flag
             }
         } else {
         // ------------- projection warps
@@ -609,7 +655,12 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 float sv;
                 if (MODE == MODE_GAP_ACC) {
                     const float y1n = sm[NGRP * WRB * GW] + (yv - acc);
-                    if (in && px >= HALO && px < HALO + own && row >= r0 && row < r1) y1o[(size_t)row * W + gpx] = y1n;
+                    if (in && px >= HALO && px < HALO + own && row >= r0 && row < r1) {
+                        const size_t idx = (size_t)row * W + gpx;
+                        y1o[idx] = y1n;
+                        if (p.y1_up != nullptr && row < p.out_lo + R) p.y1_up[idx] = y1n;
+                        if (p.y1_dn != nullptr && row >= p.out_hi - R) p.y1_dn[idx] = y1n;
+                    }
                     sv = (y1n - acc) * fast_rcp(psv);
                 } else {
                     sv = (yv - acc) * fast_rcp(psv);
@@ -629,6 +680,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             }
         }
         }   // segments
+        if (p.y1_up != nullptr || p.y1_dn != nullptr) __threadfence_system();               // pushed y1 rows before the flag
         if (p.prof && lane == 0) {
             long long* pr = p.prof + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * 4;
             pr[0] = clock64() - pstart; pr[1] = pw0; pr[2] = pw1; pr[3] = pw2;
@@ -636,8 +688,10 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
         }   // projection warps
     }
 
-    // ---- skimage's stopping rule, replayed by the last CTA on the accumulated energies
-    if (p.flag != nullptr) {
+    // ---- the last CTA: skimage's stopping rule replayed on the accumulated energies; the neighbours' flags
+    const bool want_energy = p.flag != nullptr || p.energy_log != nullptr;
+    const bool want_signal = p.sig_up != nullptr || p.sig_dn != nullptr;
+    if (want_energy || want_signal) {
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
@@ -648,22 +702,36 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
         __syncthreads();
         if (s_last) {
             __threadfence();
-            const int nslice = p.B * C;
-            bool fired = false;
-            for (int s = tid; s < nslice; s += blockDim.x) {
-                volatile double* e = p.energy + (size_t)s * R;
-                double ev[R];
+            if (want_energy) {
+                const int nslice = p.B * C;
+                bool fired = false;
+                for (int s = tid; s < nslice; s += blockDim.x) {
+                    volatile double* e = p.energy + (size_t)s * R;
+                    double ev[R];
 #pragma unroll
-                for (int i = 0; i < R; ++i) { ev[i] = e[i]; e[i] = 0.0; }     // leave the accumulators clean
-                double e_prev = ev[0];
+                    for (int i = 0; i < R; ++i) { ev[i] = e[i]; e[i] = 0.0; }     // leave the accumulators clean
+                    if (p.energy_log != nullptr) {
 #pragma unroll
-                for (int i = 1; i < R; ++i) {                                   // a stop at i = R changes nothing
-                    if (fabs(e_prev - ev[i]) < p.tv_eps * ev[0]) fired = true;
-                    e_prev = ev[i];
+                        for (int i = 0; i < R; ++i) p.energy_log[(size_t)s * R + i] = ev[i];
+                    }
+                    double e_prev = ev[0];
+#pragma unroll
+                    for (int i = 1; i < R; ++i) {                                   // a stop at i = R changes nothing
+                        if (fabs(e_prev - ev[i]) < p.tv_eps * ev[0]) fired = true;
+                        e_prev = ev[i];
+                    }
+                }
+                if (fired && p.flag != nullptr) atomicOr(p.flag, 1);
+            }
+            if (tid == 0) {
+                *p.ticket = 0u;
+                if (want_signal) {
+                    // every CTA's pushed rows are behind its ticket (bulk_wait / __threadfence_system above)
+                    __threadfence_system();
+                    if (p.sig_up != nullptr) st_release_sys(p.sig_up, p.sig_epoch);
+                    if (p.sig_dn != nullptr) st_release_sys(p.sig_dn, p.sig_epoch);
                 }
             }
-            if (fired) atomicOr(p.flag, 1);
-            if (tid == 0) *p.ticket = 0u;
         }
     }
 }

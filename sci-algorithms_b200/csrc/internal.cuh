@@ -53,6 +53,23 @@ struct FusedArgs {
     int e_lo = 0, e_hi = 0;
     bool accumulate_only = false;   // leave the energies in the workspace: no check, no reset (flag is ignored)
     bool skip_clear = false;        // the workspace slot is already zero
+    // Warp-specialised kernel only: produce rows [out_lo, out_hi) of the H local rows (out_hi == 0: all of them), keep
+    // this launch's [B][C][R] energies in energy_log, push the rows next to a tile seam to the neighbours (TilePush).
+    int out_lo = 0, out_hi = 0;
+    double* energy_log = nullptr;
+    const struct TilePush* push = nullptr;
+};
+// Halo push of the row-tiled mode (gap_tv_ws.cuh): the neighbours' OUTPUT buffers of this iteration (IPC-mapped),
+// their local row counts and the global row of their local row 0, the flags.
+struct TilePush {
+    float* x_up = nullptr; float* x_dn = nullptr;         // neighbour's x_out (null: no neighbour on that side)
+    float* y1_up = nullptr; float* y1_dn = nullptr;       // neighbour's y1_out (accelerated GAP)
+    int up_rows = 0, dn_rows = 0;                         // local rows of the neighbours' buffers
+    int up_shift = 0, dn_shift = 0;                       // my local row + shift = the neighbour's local row
+    const int* wait_up = nullptr; const int* wait_dn = nullptr;
+    int* sig_up = nullptr; int* sig_dn = nullptr;
+    int wait_epoch = 0, sig_epoch = 0;
+    int* timeout_flag = nullptr;
 };
 bool fused_supported(int mode, int B, int H, int W, int C, int tv_iter_max);
 bool fused_cassi_supported(int mode, int B, int H, int W, int C, int tv_iter_max);

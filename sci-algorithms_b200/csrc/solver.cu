@@ -21,6 +21,8 @@ using namespace scipnp;
 
 namespace {
 constexpr int kPsnrCap = 1 << 16;
+constexpr int kElogCap = 1024;      // iterations per run whose TV energies are kept for the cross-rank stopping rule
+constexpr int kSyncInts = 16;
 }
 
 struct scipnp_solver {
@@ -56,6 +58,7 @@ struct scipnp_solver {
         float* y1[2] = {nullptr, nullptr};
         int* sync = nullptr;                  // the neighbour's flag block
         int row_lo = 0;                       // global row of the neighbour's local row 0
+        int rows = 0;                         // the neighbour's local row count (halo push)
         void* mapped[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     };
     bool tiled = false;
@@ -63,8 +66,14 @@ struct scipnp_solver {
     float* xbuf[2] = {nullptr, nullptr};      // identity of my own two x / y1 buffers
     float* y1buf[2] = {nullptr, nullptr};
     int* sync = nullptr;                      // [0] ready<-up [1] ready<-down [2] ack<-up [3] ack<-down [4] timeout
+                                              // [5] pull counter [8] pushed<-up [9] pushed<-down
     int epoch = 0;
     bool ack_pending = false;
+    // halo push (gap_tv_ws.cuh): one exchange per iteration inside the fused kernel, no exchange kernel
+    bool push_enabled = false;
+    int push_epoch = 0;                       // fused push steps so far = the value every rank's flags reach
+    double* elog = nullptr;                   // [kElogCap][B*C*R] energies of the iterations since begin()
+    int elog_count = 0;
     TvTiling tv_tiling;                       // owned rows + cross-rank energy sum for the exact path's stopping rule
     PeerLink up, dn;
 
@@ -274,7 +283,36 @@ static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
         a.mode = MODE_ADMM;
         a.b_in = s->ba; a.b_out = s->bb; a.xproj_out = s->xproj;
     }
+    TilePush tp{};
+    const bool push = s->tiled && s->push_enabled && (s->up.present || s->dn.present);
+    if (s->tiled && s->push_enabled) {
+        // owned rows only; the halo rows of the output buffers are written by the neighbours
+        a.out_lo = s->t_lo - s->t_row_lo;
+        a.out_hi = s->t_hi - s->t_row_lo;
+        const int slot = k - s->begin_iter;
+        if (s->elog && slot >= 0 && slot < kElogCap) {
+            a.energy_log = s->elog + (size_t)slot * p.B * p.C * (p.tv_iter_max - 1);
+            if (slot + 1 > s->elog_count) s->elog_count = slot + 1;
+        }
+    }
+    if (push) {
+        const int xo = s->xb == s->xbuf[0] ? 0 : 1, yo = s->y1b == s->y1buf[0] ? 0 : 1;
+        if (s->up.present) {
+            tp.x_up = s->up.x[xo]; tp.y1_up = p.accelerate ? s->up.y1[yo] : nullptr;
+            tp.up_rows = s->up.rows; tp.up_shift = s->t_row_lo - s->up.row_lo;
+            tp.wait_up = s->sync + 8; tp.sig_up = s->up.sync + 9;
+        }
+        if (s->dn.present) {
+            tp.x_dn = s->dn.x[xo]; tp.y1_dn = p.accelerate ? s->dn.y1[yo] : nullptr;
+            tp.dn_rows = s->dn.rows; tp.dn_shift = s->t_row_lo - s->dn.row_lo;
+            tp.wait_dn = s->sync + 9; tp.sig_dn = s->dn.sync + 8;
+        }
+        tp.wait_epoch = s->push_epoch; tp.sig_epoch = s->push_epoch + 1;
+        tp.timeout_flag = s->sync + 4;
+        a.push = &tp;
+    }
     if (int e = launch_fused(a, st)) return e;
+    if (push) ++s->push_epoch;
     s->fws_clean = true;            // the check kernel re-zeroes the accumulators
     std::swap(s->xa, s->xb);
     if (p.method == 0) { if (p.accelerate) std::swap(s->y1a, s->y1b); }
@@ -291,6 +329,7 @@ int scipnp_solver_begin(scipnp_solver* s, void* stream) {
     if (!s->loaded) { set_error("scipnp_solver_begin before scipnp_solver_load"); return SCIPNP_ESTATE; }
     cudaStream_t st = (cudaStream_t)stream;
     s->begin_iter = s->iters_done;
+    s->elog_count = 0;
     if (!s->xsnap) return SCIPNP_OK;          // handle created without the fused path: nothing to roll back
     // A run that starts right after load() with the default initial guess needs no snapshot: a
     // rollback recomputes x0 = At(y) and clears y1 / b (saves copying the state per reconstruction).
@@ -551,8 +590,8 @@ int scipnp_solver_tiling(scipnp_solver* s, int lo, int hi, int row_lo, int row_h
     SCIPNP_REQUIRE(row_lo <= lo && lo < hi && hi <= row_hi && row_hi - row_lo == s->p.H, "inconsistent row ranges");
     s->t_lo = lo; s->t_hi = hi; s->t_row_lo = row_lo; s->t_row_hi = row_hi;
     if (!s->sync) {
-        if (int e = dmalloc(s, (void**)&s->sync, 8 * sizeof(int))) return e;
-        SCIPNP_CUDA(cudaMemset(s->sync, 0, 8 * sizeof(int)));
+        if (int e = dmalloc(s, (void**)&s->sync, kSyncInts * sizeof(int))) return e;
+        SCIPNP_CUDA(cudaMemset(s->sync, 0, kSyncInts * sizeof(int)));
     }
     s->tiled = true;
     s->epoch = 0;
@@ -680,6 +719,19 @@ int scipnp_solver_run_tiled(scipnp_solver* s, int iters, int k, void* stream) {
     SCIPNP_REQUIRE(iters >= 0 && k >= 1, "bad iteration counts");
     if (!s->tiled) { set_error("not a tiled solver"); return SCIPNP_ESTATE; }
     cudaStream_t st = (cudaStream_t)stream;
+    if (s->push_enabled && s->use_fused && k == 1) {
+        // Halo push: every fused launch stores the rows next to a seam into the neighbours' halo rows and raises
+        // their flags; the next launch's loader waits for mine.  Nothing but the iterations is enqueued.
+        if (int e = scipnp_solver_step_async(s, iters, stream)) return e;
+        if (s->up.present || s->dn.present) {
+            // my halo rows are complete (and nobody writes my buffers any more) once both flags reached the step count
+            tile_wait_kernel<<<1, 1, 0, st>>>(s->up.present ? s->sync + 8 : nullptr, s->dn.present ? s->sync + 9 : nullptr,
+                                             s->push_epoch, s->sync + 4);
+            count_launch();
+            if (int e = check_launch("tile_wait_kernel")) return e;
+        }
+        return SCIPNP_OK;
+    }
     for (int it = 0; it < iters; ++it) {
         // The neighbours pull from the buffer the state was in at the last exchange.  The fused step ping-pongs, so
         // it is the step after next that overwrites that buffer: their acknowledgement must be in by the second step
@@ -694,6 +746,48 @@ int scipnp_solver_run_tiled(scipnp_solver* s, int iters, int k, void* stream) {
     // When the stream has drained the neighbours are done reading my buffers: a following load(), rollback or
     // owned() copy may touch them without another rendezvous.
     if (int e = tile_wait_ack(s, st)) return e;
+    return SCIPNP_OK;
+}
+
+// Halo push for a tiled handle whose halo is exactly tv_iter_max-1 rows per neighbour (one exchange per iteration):
+// `up_rows` / `dn_rows` are the neighbours' local row counts.  Takes effect in scipnp_solver_run_tiled(k = 1) while
+// the handle is on the fused path; the exact path keeps the pull exchange.
+int scipnp_solver_enable_push(scipnp_solver* s, int up_rows, int dn_rows) {
+    SCIPNP_REQUIRE(s, "null solver");
+    if (!s->tiled) { set_error("call scipnp_solver_tiling first"); return SCIPNP_ESTATE; }
+    const scipnp_params& p = s->p;
+    const int R = p.tv_iter_max - 1;
+    FusedArgs a{};
+    a.mode = p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN;
+    a.B = p.B; a.H = p.H; a.W = p.W; a.C = p.C; a.tv_iter_max = p.tv_iter_max;
+    a.x_in = s->xa; a.x_out = s->xb; a.Phi = s->Phi; a.y = s->y; a.Phi_sum = s->PhiSum; a.y1_in = s->y1a; a.y1_out = s->y1b;
+    if (!s->fused_possible || !s->xb || !fused_ws_supported(a)) {
+        set_error("halo push needs the warp-specialised fused kernel (GAP, C %% 4 == 0, C <= 24, W %% 4 == 0)");
+        return SCIPNP_ESTATE;
+    }
+    if ((s->up.present && (s->t_lo - s->t_row_lo != R || up_rows < 1)) ||
+        (s->dn.present && (s->t_row_hi - s->t_hi != R || dn_rows < 1)) || s->t_hi - s->t_lo < R) {
+        set_error("halo push needs exactly tv_iter_max-1 halo rows per neighbour and at least as many owned rows");
+        return SCIPNP_EINVAL;
+    }
+    s->up.rows = up_rows; s->dn.rows = dn_rows;
+    if (!s->elog) {
+        if (int e = dmalloc(s, (void**)&s->elog, (size_t)kElogCap * p.B * p.C * R * sizeof(double))) return e;
+    }
+    s->push_enabled = true;
+    return SCIPNP_OK;
+}
+
+int scipnp_solver_uses_push(scipnp_solver* s) { return s && s->push_enabled ? 1 : 0; }
+
+// TV energies [iterations][B*C][tv_iter_max-1] of the fused iterations since scipnp_solver_begin, summed over this
+// rank's owned rows (device memory; valid once the stream has drained).  A tiled caller sums them over the ranks and
+// applies skimage's stopping rule to the whole scene.
+int scipnp_solver_energy_log(scipnp_solver* s, double** dev, int* iterations, int* per_iteration) {
+    SCIPNP_REQUIRE(s && dev && iterations && per_iteration, "null pointer");
+    *dev = s->elog;
+    *iterations = s->elog ? s->elog_count : 0;
+    *per_iteration = s->p.B * s->p.C * (s->p.tv_iter_max - 1);
     return SCIPNP_OK;
 }
 

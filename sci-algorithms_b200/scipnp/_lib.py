@@ -88,6 +88,9 @@ _SIGS = {
     "scipnp_solver_ipc_export": (C.c_int, [_vp, C.c_char_p]),
     "scipnp_solver_ipc_attach": (C.c_int, [_vp, _i, C.c_char_p, _i]),
     "scipnp_solver_set_energy_reduce": (C.c_int, [_vp, _vp, _vp, C.c_longlong]),
+    "scipnp_solver_enable_push": (C.c_int, [_vp, _i, _i]),
+    "scipnp_solver_uses_push": (C.c_int, [_vp]),
+    "scipnp_solver_energy_log": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_i)]),
     "scipnp_solver_exchange": (C.c_int, [_vp, _vp]),
     "scipnp_solver_run_tiled": (C.c_int, [_vp, _i, _i, _vp]),
     "scipnp_solver_sync_error": (C.c_int, [_vp, C.POINTER(_i), _vp]),

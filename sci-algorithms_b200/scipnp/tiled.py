@@ -113,6 +113,9 @@ class TiledSolver:
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.exchanges = 0
         self.transport = "nccl"
+        self.push = False          # halo push inside the fused kernel (p2p transport, exchange_every = 1)
+        self.tv_eps = float(tv_eps)
+        self.R = int(tv_iter_max) - 1
         if world > 1:
             self._setup_energy_reduce()
         if transport in ("p2p", "auto") and world > 1:
@@ -171,6 +174,17 @@ class TiledSolver:
             self.transport = "p2p"
         elif required:
             raise RuntimeError("peer-to-peer halo transport unavailable: %s" % (err or "halo wider than a block"))
+        if self.transport == "p2p" and self.k == 1 and self.solver.uses_fused:
+            # one exchange per iteration: let the fused kernel push its seam rows itself (no exchange kernel)
+            rows = [p[3] - p[2] for p in plan]
+            up = rows[self.rank - 1] if self.rank > 0 else 0
+            dn = rows[self.rank + 1] if self.rank + 1 < self.world else 0
+            ok = 1 if lib.scipnp_solver_enable_push(self.solver._h, up, dn) == 0 else 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            self.push = bool(int(flag.item()))
+            if ok and not self.push:
+                raise RuntimeError("halo push could be set up on some ranks only")
 
     # -- data ----------------------------------------------------------------------------
     def load(self, y_local, Phi_local, x0_local=None, X_orig_local=None):
@@ -214,10 +228,14 @@ class TiledSolver:
             self._check_sync()
         if not fused:
             return
-        flag = torch.tensor([1 if self.solver.fired() else 0], dtype=torch.int32, device=self.device)
-        if self.world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
-        if int(flag.item()):
+        if self.push:
+            fired = self._stop_rule_whole_scene(iters)
+        else:
+            flag = torch.tensor([1 if self.solver.fired() else 0], dtype=torch.int32, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            fired = bool(int(flag.item()))
+        if fired:
             self.solver.rollback()
             self.solver.set_path(False)
             try:
@@ -225,6 +243,32 @@ class TiledSolver:
             finally:
                 self.solver.set_path(True)
             self.solver.add_refined(iters)
+
+    def _stop_rule_whole_scene(self, iters):
+        """skimage's eps test (pnp_sci_algo.py:650 -> denoise_tv_chambolle) on the energies of the WHOLE scene: the
+        fused kernel logs the energies of every iteration over this rank's owned rows; one all-reduce per run sums
+        them over the ranks, and every rank takes the same decision."""
+        import ctypes as ct
+        from ._lib import lib, check
+        dev, n, per = ct.c_void_p(), ct.c_int(0), ct.c_int(0)
+        check(lib.scipnp_solver_energy_log(self.solver._h, ct.byref(dev), ct.byref(n), ct.byref(per)))
+        fired_local = 0
+        if n.value < iters:              # log capacity exceeded: fall back to the per-tile side check for the rest
+            fired_local = 1 if self.solver.fired() else 0
+        if n.value > 0 and self.R > 1:
+            e = _wrap(dev.value, (n.value, per.value // self.R, self.R), self.device, "<f8").clone()
+        else:
+            e = torch.zeros((1, 1, max(self.R, 1)), dtype=torch.float64, device=self.device)
+        tail = torch.tensor([float(fired_local)], dtype=torch.float64, device=self.device)
+        buf = torch.cat([e.reshape(-1), tail])
+        if self.world > 1:
+            dist.all_reduce(buf, group=self.group)
+        e = buf[:-1].reshape(e.shape)
+        fired = bool(buf[-1].item() > 0)
+        if n.value > 0 and self.R > 1:
+            hit = (e[..., :-1] - e[..., 1:]).abs() < self.tv_eps * e[..., 0:1]
+            fired = fired or bool(hit.any().item())
+        return fired
 
     def _check_sync(self):
         import ctypes as ct

@@ -45,7 +45,7 @@ def _worker(rank, world, port, H, W, C, iters, k, fused, tv_eps, method, out_dir
         ts.run(iters // 2)
         ts.run(iters - iters // 2)             # two runs: halos must be fresh at a run boundary
         np.save(os.path.join(out_dir, "x_%d.npy" % rank), ts.result().cpu().numpy())
-        np.save(os.path.join(out_dir, "meta_%d.npy" % rank), np.array([ts.refined_iters, int(ts.uses_fused)]))
+        np.save(os.path.join(out_dir, "meta_%d.npy" % rank), np.array([ts.refined_iters, int(ts.uses_fused), int(ts.push)]))
         ts.close()
     finally:
         dist.destroy_process_group()
@@ -78,7 +78,30 @@ def test_p2p_tiled_equals_single_gpu(sp, tmp_path, world, k):
     got, meta = _tiled(tmp_path, world, H, W, C, iters, k)
     ref, refined = _single(H, W, C, iters)
     assert refined == 0 and (meta[:, 0] == 0).all() and (meta[:, 1] == 1).all()
+    # one exchange per iteration = the halo push inside the fused kernel (what bench.py measures at N > 1)
+    assert (meta[:, 2] == (1 if k == 1 else 0)).all()
     assert float(np.abs(got - ref).max()) <= 1e-6
+
+
+@pytest.mark.parametrize("world,H,W,C,T", [(2, 96, 3840, 24, 5), (3, 150, 256, 8, 4), (4, 64, 512, 12, 5), (2, 41, 64, 4, 3)])
+def test_push_tiled_shapes(sp, tmp_path, world, H, W, C, T):
+    """Halo push (k = 1) on the bench's tile width and on ragged row counts / other channel counts and dual
+    iteration counts: the seam rows written by the neighbours' TMA stores, the y1 rows by plain peer stores."""
+    got, meta = _tiled(tmp_path, world, H, W, C, 6, 1, T=T)
+    ref, refined = _single(H, W, C, 6, T=T)
+    assert refined == 0 and (meta[:, 1] == 1).all() and (meta[:, 2] == 1).all()
+    assert float(np.abs(got - ref).max()) <= 1e-6
+
+
+def test_push_tiled_rollback_whole_scene_rule(sp, tmp_path):
+    """k = 1 (push) with an eps at which skimage's rule fires: the decision is taken on the energies of the whole
+    scene (the per-iteration log summed over the ranks), every rank rolls back, the exact path (pull exchange)
+    redoes the run with the single-GPU stopping decisions."""
+    H, W, C, iters = 136, 128, 8, 4
+    got, meta = _tiled(tmp_path, 2, H, W, C, iters, 1, tv_eps=0.5)
+    ref, refined = _single(H, W, C, iters, tv_eps=0.5)
+    assert refined == iters and (meta[:, 0] == iters).all() and (meta[:, 2] == 1).all()
+    assert float(np.abs(got - ref).max()) <= 2e-6
 
 
 @pytest.mark.parametrize("k", [1, 2])
