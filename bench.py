@@ -323,6 +323,40 @@ def measure_configs(torch, peak):
     return out
 
 
+def measure_c2_sharded(torch, dist, rank, world):
+    """BASELINE config 2 at N GPUs: the 28 coded frames of the six grayscale benchmarks dealt round-robin over the
+    ranks (scipnp.sharded.shard_indices), every rank solving its frames as one ADMM-TV batch; no collective on the
+    data path.  Timed on the device, max over ranks; each rank's frames are compared with a solve of all 28 frames
+    on the same GPU (independent batch elements: expected identical)."""
+    from scipnp import synth
+    from scipnp.engine import Solver
+    from scipnp.sharded import shard_indices
+    F = 28
+    scenes = [synth.make_cacti(256, 256, 8, 1, cfg=20 + i) for i in range(F)]
+    yb = np.stack([m[:, :, 0] / np.float32(255.) for m, _, _ in scenes])
+    pb = np.stack([k for _, k, _ in scenes])
+    mine = shard_indices(F, world, rank)
+    kw = dict(method="admm", gamma=0.01, tv_weight=0.3, tv_iter_max=5, phi_batched=True)
+    with Solver(len(mine), 256, 256, 8, **kw) as so:
+        so.load(yb[mine], pb[mine])
+        dist.barrier()
+        ms = _time_run(torch, so.run, ITERS)
+        so.load(yb[mine], pb[mine])
+        so.run(ITERS)
+        x_mine = so.get_x()
+    with Solver(F, 256, 256, 8, **kw) as so:
+        so.load(yb, pb)
+        so.run(ITERS)
+        x_all = so.get_x()
+    t = torch.tensor([ms, float(np.abs(x_mine - x_all[mine]).max())], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, err = float(t[0]), float(t[1])
+    return {"workload": "c2 ADMM-TV, 28 coded frames 256x256xCr=8 dealt round-robin over %d GPUs (%d-%d frames per "
+                        "rank), one batched solve per rank, no collective" % (world, F // world, -(-F // world)),
+            "ms_per_iteration": ms, "frame_iterations_per_s": F * 1e3 / ms,
+            "parity": {"max_abs_vs_one_gpu_batch": err, "iterations": ITERS, "tolerance": "identical"}}
+
+
 # -- our arm -----------------------------------------------------------------------------------
 
 def run_ours(args):
@@ -415,6 +449,8 @@ def run_ours(args):
         del ref, yf, Pf, xr
         torch.cuda.empty_cache()
 
+    sharded = measure_c2_sharded(torch, dist, rank, world) if world > 1 else None
+
     # -- end to end through the host-buffer C ABI (N = 1) or the tiled host path ----------------
     e2e = None
     if world == 1:
@@ -497,6 +533,8 @@ def run_ours(args):
             configs = measure_configs(torch, peak)
     elif tiled_parity is not None:
         parity = {"tiled": tiled_parity}
+    if sharded is not None:
+        configs = {"c2_sharded": sharded}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,

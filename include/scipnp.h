@@ -277,6 +277,7 @@ int scipnp_solver_ipc_attach(scipnp_solver *s, int side, const unsigned char *bl
 int scipnp_solver_exchange(scipnp_solver *s, void *stream);
 int scipnp_solver_run_tiled(scipnp_solver *s, int iters, int k, void *stream);
 int scipnp_solver_sync_error(scipnp_solver *s, int *timed_out, void *stream);
+int scipnp_solver_sync_flag(scipnp_solver *s, int **dev);   /* device address of that flag (NULL before _tiling) */
 /* skimage's stopping rule of the TV step (pnp_sci_algo.py:650 -> denoise_tv_chambolle) compares energies summed
  * over the WHOLE image.  On the exact path a tiled handle sums its owned rows only and hands the 2*C partial
  * energies of every dual iteration (device doubles) to `reduce`, which must sum them over all ranks in place,

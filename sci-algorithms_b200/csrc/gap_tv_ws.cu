@@ -123,13 +123,13 @@ bool fused_ws_supported(const FusedArgs& a) {
 
 // Owned pixels per group and grid size.  The kernel deals the (batch x strips x charged rows) units out evenly
 // (WsSegIter), so the grid is one CTA per SM on large scenes; small scenes get segments of about 8 units.
-static void ws_split(int B, int H, int W, int Q, int* own_out, int* grid_out) {
+static void ws_split(int B, int H, int W, int Q, int cost, int* own_out, int* grid_out) {
     const int NGRP = ws_groups(Q), nsm = num_sms();
     long long best = -1;
     int bown = OWN_MAX, bgrid = 1;
     for (int own = OWN_MAX; own >= 32; own -= 4) {
         const int ngroups = (W + own - 1) / own, nstrips = (ngroups + NGRP - 1) / NGRP;
-        const long long total = (long long)B * nstrips * (H + kWsSegCost);
+        const long long total = (long long)B * nstrips * (H + cost);
         long long grid = total / 8;          // small scenes: 256x256x8 measured 47 us at 32 units per CTA, 28 us at 8, 30 us at 4
         if (grid > nsm) grid = nsm;
         if (grid < 1) grid = 1;
@@ -158,7 +158,9 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
     if (p.out_lo < 0 || p.out_hi > a.H || p.out_lo >= p.out_hi) { set_error("bad output row window"); return SCIPNP_EINVAL; }
     p.energy_log = a.energy_log;
     int own = OWN_MAX, grid = 1;
-    ws_split(a.B, p.out_hi - p.out_lo, a.W, Q, &own, &grid);
+    p.seg_cost = kWsSegCost;
+    if (const char* e = getenv("SCIPNP_WS_SEGCOST")) { int v = atoi(e); if (v >= 0 && v <= 256) p.seg_cost = v; }
+    ws_split(a.B, p.out_hi - p.out_lo, a.W, Q, p.seg_cost, &own, &grid);
     if (const char* e = getenv("SCIPNP_WS_OWN")) { int v = atoi(e); if (v >= 4 && v <= OWN_MAX && v % 4 == 0) own = v; }
     if (const char* e = getenv("SCIPNP_WS_GRID")) { int v = atoi(e); if (v >= 1) grid = v; }
     p.own = own;

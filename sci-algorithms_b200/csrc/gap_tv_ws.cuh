@@ -40,6 +40,15 @@ using namespace fusedk;     // PTX helpers, P2 arithmetic
 #define WS_CREGS 0        // > 0: setmaxnreg -- consumers WS_CREGS registers, producers WS_PREGS (12*C + 4*P <= 2048)
 #define WS_PREGS 0
 #endif
+#ifndef WS_GEN_UNROLL
+#define WS_GEN_UNROLL 0   // 1: the masked (first / last) blocks of a row segment are unrolled like the steady-state ones
+#endif
+#ifndef WS_PATH3
+#define WS_PATH3 1        // 1: first / last blocks of a row segment whose rows all exist take an unrolled path with energy masks only
+#endif
+#ifndef WS_SANITIZE
+#define WS_SANITIZE 0     // 1: every lane arrives on the mbarriers (counts x 32) instead of one elected lane behind a __syncwarp:
+#endif                    // same protocol, but visible thread by thread to compute-sanitizer's racecheck (tools/sanitize.sh)
 #ifndef WS_EXP
 #define WS_EXP 0          // timing experiments (bit flags; results are meaningless): 1 independent stages, 2 no out-tile
 #endif                    // stores, 4 no energies, 8 no shuffles
@@ -69,6 +78,7 @@ struct WsParams {
     // Output row window [out_lo, out_hi) inside the H local rows (the whole scene: [0, H)).  A rank of the row-tiled
     // multi-GPU mode produces its owned rows only; the rows outside the window are halo rows, input only.
     int out_lo, out_hi;
+    int seg_cost;                 // rows a strip is charged in the work split for starting a row segment (kWsSegCost)
     double* energy_log;           // this launch's [B][C][R] energies are also left here (null: not kept)
     // ---- halo push (row-tiled mode, one exchange per iteration, no exchange kernel): the R owned rows next to a
     // seam are stored a second time, into the neighbour's halo rows of ITS output buffers (CUDA-IPC mapped, NVLink);
@@ -197,11 +207,14 @@ struct WsConst {
 // PATH 1 (fast): every row touched lies inside [r0, r1) and the image and the whole group lies inside the image.
 // PATH 2 (edge): the rows as in 1, but the group hangs over the left or right image edge: pixel masks only.
 // PATH 0 (general): row masks and pixel masks.
+// PATH 3 (energy window): rows and pixels as in 1 -- every row touched exists and lies inside the image -- but rows outside
+//        [r0, r1) (warm-up rows above the segment, drain rows below it) must stay out of the energy sums.
 template <int R, int PATH>
 __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, const P2 (&f_new)[2], const P2 (&f_old)[2],
                                         P2 (&o_out)[2]) {
     constexpr bool FAST = PATH != 0;          // no row masks
-    constexpr bool PXM = PATH != 1;           // pixel masks
+    constexpr bool PXM = PATH == 0 || PATH == 2;   // pixel masks
+    constexpr bool EM = PATH == 3;            // energy masks only
     P2 o_new[2] = {f_new[0], f_new[1]};
     P2 o_last[2] = {f_new[0], f_new[1]};
     P2 pi0[2], pi1[2];
@@ -215,6 +228,10 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
         if (!FAST) {
             m2 = splat(((u >= c.rs) && (u < c.H)) ? c.pair_in : 0.f);
             md2 = splat(row_new < c.H ? 1.f : 0.f);
+            const float me = (u >= c.r0 && u < c.r1) ? 1.f : 0.f;
+            me2 = splat(me);
+            wm2 = splat(me * c.tvw);
+        } else if (EM) {
             const float me = (u >= c.r0 && u < c.r1) ? 1.f : 0.f;
             me2 = splat(me);
             wm2 = splat(me * c.tvw);
@@ -279,7 +296,7 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
         }
         if (!(FAST && (WS_EXP & 4)))
         if (i + 1 < R) {
-            if (FAST) {
+            if (FAST && !EM) {
                 S.en[i + 1] = fma2(d[0], d[0], S.en[i + 1]);
                 S.en[i + 1] = fma2(d[1], d[1], S.en[i + 1]);
             } else {
@@ -316,18 +333,19 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
 // Work of one CTA: the scene is (batch x column strips) strips of H rows laid end to end, every strip charged
 // kSegCost extra units in front of its rows; a CTA takes `per_cta` consecutive units, i.e. a few row segments of
 // neighbouring strips (one or two on large scenes).  No wave quantisation: every SM gets the same share.
-constexpr int kWsSegCost = 16;    // cost of starting a row segment, in rows (warm-up + drain rows, pipeline fill)
+constexpr int kWsSegCost = 8;     // cost of starting a row segment, in rows (warm-up + drain rows); 278-row tiles: 8..12 best, 16 +2 %
 template <int R>
 struct WsSegIter {
     long long unit, unit_end;
-    int Hv, H, lo, nstrips;
+    int Hv, H, lo, cost, nstrips;
     int b, strip, r0, r1, rs, t_end, nblk;      // current segment
     __device__ WsSegIter(const WsParams& p, int per_cta_unused = 0) {
-        H = p.H; lo = p.out_lo; Hv = (p.out_hi - p.out_lo) + kWsSegCost; nstrips = p.nstrips;
+        H = p.H; lo = p.out_lo; cost = p.seg_cost; Hv = (p.out_hi - p.out_lo) + cost; nstrips = p.nstrips;
+        // total = q * grid + rem: the first `rem` CTAs take q + 1 units, the others q
         const long long total = (long long)p.B * p.nstrips * Hv;
-        const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
-        unit = (long long)blockIdx.x * per_cta;
-        unit_end = unit + per_cta < total ? unit + per_cta : total;
+        const long long q = total / gridDim.x, rem = total - q * gridDim.x, c = blockIdx.x;
+        unit = c * q + (c < rem ? c : rem);
+        unit_end = unit + q + (c < rem ? 1 : 0);
     }
     __device__ bool next() {
         while (unit < unit_end) {
@@ -336,8 +354,8 @@ struct WsSegIter {
             const long long left = unit_end - unit;
             const int v1 = (long long)(Hv - v0) < left ? Hv : v0 + (int)left;
             unit += v1 - v0;
-            r0 = lo + (v0 - kWsSegCost > 0 ? v0 - kWsSegCost : 0);
-            r1 = lo + v1 - kWsSegCost;
+            r0 = lo + (v0 - cost > 0 ? v0 - cost : 0);
+            r1 = lo + v1 - cost;
             if (r1 <= r0) continue;                                  // only charge units: no rows here
             b = s / nstrips;
             strip = s - b * nstrips;
@@ -371,9 +389,10 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
     const uint32_t bar_ofull = bar_fempty + 8 * NF;
     const uint32_t bar_oempty = bar_ofull + 8 * NOUT;
     if (tid == 0) {
-        for (int i = 0; i < NRAW; ++i) { mbar_init(bar_raw + 8 * i, 1); mbar_init(bar_rempty + 8 * i, NCOMP); }
-        for (int i = 0; i < NF; ++i) { mbar_init(bar_ffull + 8 * i, NCOMP); mbar_init(bar_fempty + 8 * i, CW); }
-        for (int i = 0; i < NOUT; ++i) { mbar_init(bar_ofull + 8 * i, CW); mbar_init(bar_oempty + 8 * i, 1); }
+        constexpr int kArr = WS_SANITIZE ? 32 : 1;       // arrivals per warp
+        for (int i = 0; i < NRAW; ++i) { mbar_init(bar_raw + 8 * i, 1); mbar_init(bar_rempty + 8 * i, NCOMP * kArr); }
+        for (int i = 0; i < NF; ++i) { mbar_init(bar_ffull + 8 * i, NCOMP * kArr); mbar_init(bar_fempty + 8 * i, CW * kArr); }
+        for (int i = 0; i < NOUT; ++i) { mbar_init(bar_ofull + 8 * i, CW * kArr); mbar_init(bar_oempty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         fence_async_smem();
     }
@@ -462,12 +481,21 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     }
                 }
             };
+            // every row touched exists (warm-up done, f(t-R) in the ring) and lies inside the image; steps past t_end
+            // are harmless there (their rows are neither stored nor counted)
+            const bool rows_em = WS_PATH3 && t0 - R >= rs && t0 + WRB - 1 <= H - 1;
             if (rows_fast && interior) {
                 fast_block(std::integral_constant<int, 1>{});
             } else if (rows_fast) {
                 fast_block(std::integral_constant<int, 2>{});
+            } else if (rows_em && interior) {
+                fast_block(std::integral_constant<int, 3>{});
             } else {
+#if WS_GEN_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
                 for (int j = 0; j < WRB; ++j) {
                     const int t = t0 + j;
                     if (t < t_end) {
@@ -489,7 +517,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             }
             fence_async_smem();                  // the TMA store reads what this warp just wrote
             __syncwarp();
-            if (lane == 0) {
+            if (WS_SANITIZE || lane == 0) {
                 mbar_arrive(bar_ofull + 8 * os);
                 // the last stage reads f(t-R) out of the previous block's slot: a slot is handed back one block late,
                 // the last one of a segment together with its predecessor
@@ -674,7 +702,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 }
             }
             __syncwarp();
-            if (lane == 0) {
+            if (WS_SANITIZE || lane == 0) {
                 mbar_arrive(bar_ffull + 8 * fs);
                 mbar_arrive(bar_rempty + 8 * slot);          // this warp is done reading the raw slot
             }

@@ -791,6 +791,14 @@ int scipnp_solver_energy_log(scipnp_solver* s, double** dev, int* iterations, in
     return SCIPNP_OK;
 }
 
+// device address of the time-out flag (an int, nonzero after a neighbour never signalled), for callers that fold it into
+// a transfer of their own instead of paying the stream drain of scipnp_solver_sync_error
+int scipnp_solver_sync_flag(scipnp_solver* s, int** dev) {
+    SCIPNP_REQUIRE(s && dev, "null pointer");
+    *dev = s->sync ? s->sync + 4 : nullptr;
+    return SCIPNP_OK;
+}
+
 int scipnp_solver_sync_error(scipnp_solver* s, int* timed_out, void* stream) {
     SCIPNP_REQUIRE(s && timed_out, "null pointer");
     *timed_out = 0;

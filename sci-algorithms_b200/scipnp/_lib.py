@@ -94,6 +94,7 @@ _SIGS = {
     "scipnp_solver_exchange": (C.c_int, [_vp, _vp]),
     "scipnp_solver_run_tiled": (C.c_int, [_vp, _i, _i, _vp]),
     "scipnp_solver_sync_error": (C.c_int, [_vp, C.POINTER(_i), _vp]),
+    "scipnp_solver_sync_flag": (C.c_int, [_vp, C.POINTER(_vp)]),
     "scipnp_solver_get_x": (C.c_int, [_vp, _fp, _vp]),
     "scipnp_solver_psnr": (C.c_int, [_vp, C.POINTER(C.c_double), _i, C.POINTER(_i), _vp]),
     "scipnp_solver_sqerr": (C.c_int, [_vp, C.POINTER(C.c_double), _i, C.POINTER(_i), _vp]),

@@ -224,7 +224,7 @@ class TiledSolver:
         if fused:
             self.solver.begin()
         self._sweep(iters)
-        if self.transport == "p2p":
+        if self.transport == "p2p" and not (self.push and fused):
             self._check_sync()
         if not fused:
             return
@@ -247,28 +247,35 @@ class TiledSolver:
     def _stop_rule_whole_scene(self, iters):
         """skimage's eps test (pnp_sci_algo.py:650 -> denoise_tv_chambolle) on the energies of the WHOLE scene: the
         fused kernel logs the energies of every iteration over this rank's owned rows; one all-reduce per run sums
-        them over the ranks, and every rank takes the same decision."""
+        them over the ranks, and every rank takes the same decision.  The neighbours' time-out flag rides along, so
+        a run costs one collective and one host synchronisation."""
         import ctypes as ct
         from ._lib import lib, check
-        dev, n, per = ct.c_void_p(), ct.c_int(0), ct.c_int(0)
+        dev, n, per, tflag = ct.c_void_p(), ct.c_int(0), ct.c_int(0), ct.c_void_p()
         check(lib.scipnp_solver_energy_log(self.solver._h, ct.byref(dev), ct.byref(n), ct.byref(per)))
-        fired_local = 0
-        if n.value < iters:              # log capacity exceeded: fall back to the per-tile side check for the rest
-            fired_local = 1 if self.solver.fired() else 0
-        if n.value > 0 and self.R > 1:
-            e = _wrap(dev.value, (n.value, per.value // self.R, self.R), self.device, "<f8").clone()
-        else:
-            e = torch.zeros((1, 1, max(self.R, 1)), dtype=torch.float64, device=self.device)
-        tail = torch.tensor([float(fired_local)], dtype=torch.float64, device=self.device)
-        buf = torch.cat([e.reshape(-1), tail])
+        check(lib.scipnp_solver_sync_flag(self.solver._h, ct.byref(tflag)))
+        have = n.value > 0 and self.R > 1
+        parts = []
+        if have:
+            parts.append(_wrap(dev.value, (n.value * per.value,), self.device, "<f8"))
+        tail = torch.zeros(2, dtype=torch.float64, device=self.device)
+        if tflag.value:
+            tail[1] = _wrap(tflag.value, (1,), self.device, "<i4")[0]
+        parts.append(tail)
+        buf = torch.cat(parts)
+        if n.value < iters:              # log capacity exceeded: the per-tile side check covers the rest
+            buf[-2] = 1.0 if self.solver.fired() else 0.0
         if self.world > 1:
             dist.all_reduce(buf, group=self.group)
-        e = buf[:-1].reshape(e.shape)
-        fired = bool(buf[-1].item() > 0)
-        if n.value > 0 and self.R > 1:
-            hit = (e[..., :-1] - e[..., 1:]).abs() < self.tv_eps * e[..., 0:1]
-            fired = fired or bool(hit.any().item())
-        return fired
+        res = buf[-2:]
+        if have:
+            e = buf[:-2].reshape(n.value, per.value // self.R, self.R)
+            hit = ((e[..., :-1] - e[..., 1:]).abs() < self.tv_eps * e[..., 0:1]).any().to(torch.float64).reshape(1)
+            res = torch.cat([res, hit])
+        res = res.tolist()               # the one host synchronisation of the run
+        if res[1] > 0:
+            raise RuntimeError("rank %d: a neighbour never signalled its halo rows (timeout)" % self.rank)
+        return res[0] > 0 or (have and res[2] > 0)
 
     def _check_sync(self):
         import ctypes as ct
