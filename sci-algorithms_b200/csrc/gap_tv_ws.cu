@@ -161,8 +161,13 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
     p.seg_cost = kWsSegCost;
     if (const char* e = getenv("SCIPNP_WS_SEGCOST")) { int v = atoi(e); if (v >= 0 && v <= 256) p.seg_cost = v; }
     ws_split(a.B, p.out_hi - p.out_lo, a.W, Q, p.seg_cost, &own, &grid);
-    if (const char* e = getenv("SCIPNP_WS_OWN")) { int v = atoi(e); if (v >= 4 && v <= OWN_MAX && v % 4 == 0) own = v; }
-    if (const char* e = getenv("SCIPNP_WS_GRID")) { int v = atoi(e); if (v >= 1) grid = v; }
+    {
+        // edge strips cost about 7 % more per row (pixel masks): their rows weigh 17/16 in the work split
+        int w = 1;
+        if (const char* e = getenv("SCIPNP_WS_EDGE")) { int v = atoi(e); if (v >= 0 && v <= 16) w = v; }
+        const int ngr = (a.W + own - 1) / own, nst = (ngr + ws_groups(Q) - 1) / ws_groups(Q);
+        p.edge_cost = nst > 2 ? w : 0;
+    }
     p.own = own;
     p.ngroups = (a.W + own - 1) / own;
     p.nstrips = (p.ngroups + ws_groups(Q) - 1) / ws_groups(Q);

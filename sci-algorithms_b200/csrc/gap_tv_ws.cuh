@@ -79,6 +79,7 @@ struct WsParams {
     // multi-GPU mode produces its owned rows only; the rows outside the window are halo rows, input only.
     int out_lo, out_hi;
     int seg_cost;                 // rows a strip is charged in the work split for starting a row segment (kWsSegCost)
+    int edge_cost;                // extra weight of a row of the first / last strip of a scene, in sixteenths of a row
     double* energy_log;           // this launch's [B][C][R] energies are also left here (null: not kept)
     // ---- halo push (row-tiled mode, one exchange per iteration, no exchange kernel): the R owned rows next to a
     // seam are stored a second time, into the neighbour's halo rows of ITS output buffers (CUDA-IPC mapped, NVLink);
@@ -334,31 +335,47 @@ __device__ __forceinline__ void ws_step(WsPipe<R>& S, const WsConst& c, int t, c
 // kSegCost extra units in front of its rows; a CTA takes `per_cta` consecutive units, i.e. a few row segments of
 // neighbouring strips (one or two on large scenes).  No wave quantisation: every SM gets the same share.
 constexpr int kWsSegCost = 8;     // cost of starting a row segment, in rows (warm-up + drain rows); 278-row tiles: 8..12 best, 16 +2 %
+constexpr int kWsTick = 16;       // work units ("ticks") per row of an interior strip
 template <int R>
 struct WsSegIter {
-    long long unit, unit_end;
-    int Hv, H, lo, cost, nstrips;
-    int b, strip, r0, r1, rs, t_end, nblk;      // current segment
+    long long unit, unit_end, Tb;
+    int Li, Le, wi, we, chg, Hw, H, lo, nstrips;    // strip lengths and row weights in ticks (interior / edge)
+    int b, strip, r0, r1, rs, t_end, nblk;          // current segment
     __device__ WsSegIter(const WsParams& p, int per_cta_unused = 0) {
-        H = p.H; lo = p.out_lo; cost = p.seg_cost; Hv = (p.out_hi - p.out_lo) + cost; nstrips = p.nstrips;
-        // total = q * grid + rem: the first `rem` CTAs take q + 1 units, the others q
-        const long long total = (long long)p.B * p.nstrips * Hv;
+        H = p.H; lo = p.out_lo; Hw = p.out_hi - p.out_lo; nstrips = p.nstrips;
+        // The first and the last strip of a scene hang over the image edge: their blocks carry pixel masks (about 7 %
+        // more instructions), so a row of theirs weighs kWsTick + edge_cost ticks instead of kWsTick.
+        wi = kWsTick; we = kWsTick + p.edge_cost; chg = p.seg_cost * kWsTick;
+        Li = chg + Hw * wi; Le = chg + Hw * we;
+        Tb = nstrips == 1 ? (long long)Le : 2LL * Le + (long long)(nstrips - 2) * Li;
+        // total = q * grid + rem: the first `rem` CTAs take q + 1 ticks, the others q
+        const long long total = (long long)p.B * Tb;
         const long long q = total / gridDim.x, rem = total - q * gridDim.x, c = blockIdx.x;
         unit = c * q + (c < rem ? c : rem);
         unit_end = unit + q + (c < rem ? 1 : 0);
     }
     __device__ bool next() {
         while (unit < unit_end) {
-            const int s = (int)(unit / Hv);
-            const int v0 = (int)(unit - (long long)s * Hv);
+            b = (int)(unit / Tb);
+            long long v = unit - (long long)b * Tb;
+            int s, len, w;
+            if (v < Le) { s = 0; len = Le; w = we; }
+            else {
+                v -= Le;
+                s = 1 + (int)(v / Li);
+                if (s >= nstrips - 1) { s = nstrips - 1; v -= (long long)(nstrips - 2) * Li; len = Le; w = we; }
+                else { v -= (long long)(s - 1) * Li; len = Li; w = wi; }
+            }
+            const int v0 = (int)v;
             const long long left = unit_end - unit;
-            const int v1 = (long long)(Hv - v0) < left ? Hv : v0 + (int)left;
+            const int v1 = (long long)(len - v0) < left ? len : v0 + (int)left;
             unit += v1 - v0;
-            r0 = lo + (v0 - cost > 0 ? v0 - cost : 0);
-            r1 = lo + v1 - cost;
-            if (r1 <= r0) continue;                                  // only charge units: no rows here
-            b = s / nstrips;
-            strip = s - b * nstrips;
+            // a row belongs to the range that holds its first tick
+            const int a0 = v0 - chg > 0 ? v0 - chg : 0, a1 = v1 - chg > 0 ? v1 - chg : 0;
+            r0 = lo + (a0 + w - 1) / w;
+            r1 = lo + (a1 + w - 1) / w;
+            if (r1 <= r0) continue;                                  // only charge ticks: no rows here
+            strip = s;
             rs = r0 - R > 0 ? r0 - R : 0;
             t_end = r1 + R;                                          // steps t in [rs, t_end)
             nblk = (t_end - rs + WRB - 1) / WRB;
