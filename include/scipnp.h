@@ -225,6 +225,9 @@ int scipnp_solver_step_async(scipnp_solver *s, int iters, void *stream);
 int scipnp_solver_fired(scipnp_solver *s, int *fired, void *stream);
 int scipnp_solver_rollback(scipnp_solver *s, void *stream);
 int scipnp_solver_set_path(scipnp_solver *s, int fused);
+/* TV weight and ADMM regulariser of the iterations that follow (ADMM_TV_rec, pnp_sci_algo.py:898-899, shrinks
+ * both every iteration). */
+int scipnp_solver_set_tv(scipnp_solver *s, double tv_weight, double gamma);
 int scipnp_solver_add_refined(scipnp_solver *s, int iters);
 
 /* Copy the current estimate (GAP: x after TV; ADMM: x before TV, as the

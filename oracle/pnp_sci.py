@@ -21,7 +21,7 @@ from .iqa import compare_psnr, compare_ssim
 
 __all__ = ["A_", "At_", "psnr", "phi_sum", "gap_denoise", "admm_denoise", "joint_admm_denoise",
            "admmdenoise_cacti", "gap_denoise_bayer", "cassi_shift_mask",
-           "cassi_shift_cube"]
+           "cassi_shift_cube", "GAP_TV_rec", "ADMM_TV_rec", "admm_denoise_bayer"]
 
 
 # -- R1 / R2 / R10 / R3 -------------------------------------------------------
@@ -99,6 +99,38 @@ def gap_denoise(y, Phi_sum, A, At, _lambda=1, accelerate=True, denoiser='tv',
                 psnr_all.append(psnr(X_orig, x))      # :682
     ps, ss = _frame_iqa(X_orig, x)
     return x, ps, ss, psnr_all
+
+
+# -- the stand-alone TV loops at the end of the module ---------------------------
+
+def GAP_TV_rec(y, Phi, A, At, Phi_sum, maxiter, step_size, weight, row, col, ColT, X_ori):
+    """Accelerated GAP with 30 Chambolle iterations per step (pnp_sci_algo.py:866-882).  ``A`` / ``At`` take the
+    mask as their second argument here (``A_`` / ``At_`` of utils.py); ``y1`` starts as float64 zeros (:867), so
+    the whole loop runs in float64 like the reference's.  The progress print (:877-881) is not restated."""
+    y1 = np.zeros((row, col))                                                   # :867
+    f = At(y, Phi)                                                              # :869
+    for ni in range(maxiter):
+        fb = A(f, Phi)                                                          # :871
+        y1 = y1 + (y - fb)                                                      # :872
+        f = f + np.multiply(step_size, At(np.divide(y1 - fb, Phi_sum), Phi))    # :873
+        f = denoise_tv_chambolle(f, weight, n_iter_max=30, multichannel=True)   # :874
+    return f
+
+
+def ADMM_TV_rec(y, Phi, A, At, Phi_sum, maxiter, step_size, weight, row, col, ColT, eta, X_ori):
+    """ADMM with 30 Chambolle iterations per step and geometrically decaying TV weight (x0.999) and
+    regulariser eta (x0.998) (pnp_sci_algo.py:884-907).  Returns ``v`` (the projection output)."""
+    theta = At(y, Phi)                                                          # :887
+    v = theta
+    b = np.zeros((row, col, ColT))                                              # :889
+    for ni in range(maxiter):
+        yb = A(theta + b, Phi)                                                  # :891
+        v = (theta + b) + np.multiply(step_size, At(np.divide(y - yb, Phi_sum + eta), Phi))   # :893
+        theta = denoise_tv_chambolle(v - b, weight, n_iter_max=30, multichannel=True)        # :895
+        b = b - (v - theta)                                                     # :897
+        weight = 0.999 * weight                                                 # :898
+        eta = 0.998 * eta                                                       # :899
+    return v
 
 
 # -- R5 -----------------------------------------------------------------------
@@ -366,6 +398,57 @@ def gap_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, accelerate=True,
 
 
 # -- R9 (spec only in the reference: DeSCI/test_desci_cassi.m:53-75) ----------
+
+def admm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denoiser='tv', iter_max=50,
+                       noise_estimate=True, sigma=None, tv_weight=0.1, tv_iter_max=5, multichannel=True,
+                       x0_bayer=None, X_orig=None, model=None, show_iqa=True):
+    """Bayer ADMM-TV (pnp_sci_algo.py:268-475).  PARITY UNPINNED: the reference's body raises NameError at :399
+    (``ball`` is never bound; :389 binds ``b`` and the sub-lattice loop then rebinds it), so it cannot be run.
+    Restated with the one evident repair -- ``ball = np.zeros_like(x0all)`` -- and otherwise statement for
+    statement: set-up :347-385, projection per sub-lattice :397-399, one TV call over the stacked channels
+    :402-406, multiplier update :427, PSNR of the merged mosaic :429-433, return :475."""
+    if denoiser.lower() != 'tv':
+        raise ValueError('Unsupported denoiser {}!'.format(denoiser))
+    bayer = [[0, 0], [0, 1], [1, 0], [1, 1]]                              # :347
+    sigma, iter_max = _as_schedule(sigma, iter_max)
+    (nrow, ncol, nmask) = Phi_bayer.shape
+    yall = np.zeros([nrow // 2, ncol // 2, 4], dtype=np.float32)
+    Phiall = np.zeros([nrow // 2, ncol // 2, nmask, 4], dtype=np.float32)
+    Phi_sumall = np.zeros([nrow // 2, ncol // 2, 4], dtype=np.float32)
+    x0all = np.zeros([nrow // 2, ncol // 2, nmask, 4], dtype=np.float32)
+    for ib, bb in enumerate(bayer):
+        yall[..., ib] = y_bayer[bb[0]::2, bb[1]::2]
+        Phiall[..., ib] = Phi_bayer[bb[0]::2, bb[1]::2]
+        Phib_sum = np.sum(Phiall[..., ib], axis=2)
+        Phib_sum[Phib_sum == 0] = 1
+        Phi_sumall[..., ib] = Phib_sum
+        if x0_bayer is None:
+            x0all[..., ib] = At_(yall[..., ib], Phiall[..., ib])
+        else:
+            x0all[..., ib] = x0_bayer[bb[0]::2, bb[1]::2]
+    xall = x0all.copy()                 # the reference aliases xall, thetaall and x0all (:386-387); the first
+    thetaall = x0all                    # projection reads theta of every sub-lattice before it writes x of it
+    x_bayer = np.zeros_like(Phi_bayer)
+    ball = np.zeros_like(x0all)         # the repair
+    psnr_all = []
+    for idx, _ in enumerate(sigma):
+        for _it in range(iter_max[idx]):
+            for ib in range(4):
+                yb = A_(thetaall[..., ib] + ball[..., ib], Phiall[..., ib])
+                xall[..., ib] = thetaall[..., ib] + ball[..., ib] + _lambda * (
+                    At_((yall[..., ib] - yb) / (Phi_sumall[..., ib] + gamma), Phiall[..., ib]))
+            v = (xall - ball).reshape([nrow // 2, ncol // 2, nmask * 4])
+            v = denoise_tv_chambolle(v, tv_weight, n_iter_max=tv_iter_max, multichannel=multichannel)
+            thetaall = v.reshape([nrow // 2, ncol // 2, nmask, 4])
+            ball = ball - (xall - thetaall)
+            if show_iqa and X_orig is not None:
+                for ib, bb in enumerate(bayer):
+                    x_bayer[bb[0]::2, bb[1]::2] = xall[..., ib]
+                psnr_all.append(psnr(X_orig, x_bayer))
+    for ib, bb in enumerate(bayer):
+        x_bayer[bb[0]::2, bb[1]::2] = xall[..., ib]
+    return x_bayer, psnr_all
+
 
 def cassi_shift_mask(mask2d, nband, step):
     """Shifted mask stack of a single-disperser CASSI system:

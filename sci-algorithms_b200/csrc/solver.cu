@@ -399,6 +399,16 @@ int scipnp_solver_rollback(scipnp_solver* s, void* stream) {
     return SCIPNP_OK;
 }
 
+// TV weight and ADMM regulariser of the iterations that follow (ADMM_TV_rec, pnp_sci_algo.py:898-899, shrinks both
+// every iteration); the other parameters stay as created.
+int scipnp_solver_set_tv(scipnp_solver* s, double tv_weight, double gamma) {
+    SCIPNP_REQUIRE(s, "null solver");
+    SCIPNP_REQUIRE(tv_weight > 0.0, "tv_weight must be positive");
+    s->p.tv_weight = tv_weight;
+    s->p.gamma = (float)gamma;
+    return SCIPNP_OK;
+}
+
 int scipnp_solver_set_path(scipnp_solver* s, int fused) {
     SCIPNP_REQUIRE(s, "null solver");
     if (fused && !s->fused_possible) { set_error("the fused path does not cover this configuration"); return SCIPNP_ESTATE; }

@@ -82,6 +82,7 @@ _SIGS = {
     "scipnp_solver_fired": (C.c_int, [_vp, C.POINTER(_i), _vp]),
     "scipnp_solver_rollback": (C.c_int, [_vp, _vp]),
     "scipnp_solver_set_path": (C.c_int, [_vp, _i]),
+    "scipnp_solver_set_tv": (C.c_int, [_vp, C.c_double, C.c_double]),
     "scipnp_solver_add_refined": (C.c_int, [_vp, _i]),
     "scipnp_solver_ipc_blob_bytes": (C.c_int, []),
     "scipnp_solver_tiling": (C.c_int, [_vp, _i, _i, _i, _i]),

@@ -271,6 +271,10 @@ class Solver:
     def set_path(self, fused):
         check(lib.scipnp_solver_set_path(self._h, 1 if fused else 0))
 
+    def set_tv(self, tv_weight, gamma=0.0):
+        """TV weight / ADMM regulariser of the iterations that follow (ADMM_TV_rec shrinks both per iteration)."""
+        check(lib.scipnp_solver_set_tv(self._h, float(tv_weight), float(gamma)))
+
     def add_refined(self, iters):
         check(lib.scipnp_solver_add_refined(self._h, int(iters)))
 

@@ -7,6 +7,9 @@ through libscipnp.so (no CPU fallback).
     admm_denoise         pnp_sci_algo.py:708-864
     admmdenoise_cacti    pnp_sci_algo.py:479-534
     gap_denoise_bayer    pnp_sci_algo.py:20-265
+    admm_denoise_bayer   pnp_sci_algo.py:268-475 (dead code in the reference; built from admm_denoise's semantics)
+    GAP_TV_rec           pnp_sci_algo.py:866-882
+    ADMM_TV_rec          pnp_sci_algo.py:884-907
     denoise_tv_chambolle skimage.restoration (imported at pnp_sci_algo.py:5)
 
 Differences from the reference, all at the boundary:
@@ -33,7 +36,8 @@ from .iqa import frames_iqa, frame_psnr, frame_ssim
 from .utils import A_, At_, psnr
 
 __all__ = ["gap_denoise", "admm_denoise", "admmdenoise_cacti", "gap_denoise_bayer",
-           "denoise_tv_chambolle", "gap_denoise_cassi", "A_", "At_", "psnr"]
+           "denoise_tv_chambolle", "gap_denoise_cassi", "A_", "At_", "psnr", "GAP_TV_rec", "ADMM_TV_rec",
+           "admm_denoise_bayer"]
 
 VERBOSE = False          # print the reference's progress lines (every 5th iteration)
 USE_FUSED = True         # one-pass fused iteration where the library supports it
@@ -218,14 +222,9 @@ def _bayer_split(a, Cc):
     return out
 
 
-def gap_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, accelerate=True, denoiser='tv',
-                      iter_max=50, noise_estimate=True, sigma=None, tv_weight=0.1,
-                      tv_iter_max=5, multichannel=True, x0_bayer=None, X_orig=None,
-                      model=None, show_iqa=True):
-    """Bayer GAP-TV (pnp_sci_algo.py:20-265): the four RGGB sub-lattices are four
-    independent measurements with their own masks; the joint TV call over the
-    [H/2, W/2, 4*Cr] stack (:163-166) is per-channel, i.e. the same batch."""
-    _check_tv(denoiser, 'tv_chambolle', multichannel)
+def _bayer_solve(method, y_bayer, Phi_bayer, x0_bayer, X_orig, show_iqa, iters, **kw):
+    """The four RGGB sub-lattices as one batch of four measurements with their own masks; returns the merged
+    mosaic (host), the device-side per-iteration squared errors and the float32 X_orig."""
     Phi = f32c(_host(Phi_bayer))
     H, W, Cc = Phi.shape
     if H % 2 or W % 2:
@@ -235,10 +234,7 @@ def gap_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, accelerate=True, denoiser='
     x0q = None if x0_bayer is None else _bayer_split(f32c(_host(x0_bayer)), Cc)
     Xo = None if X_orig is None else f32c(_host(X_orig))
     Xq = None if (Xo is None or not show_iqa) else _bayer_split(Xo, Cc)
-    iters = _total_iters(sigma, iter_max)
-    with Solver(4, H // 2, W // 2, Cc, method="gap", accelerate=accelerate, _lambda=_lambda,
-                tv_weight=tv_weight, tv_iter_max=tv_iter_max, phi_batched=True,
-                fused=USE_FUSED) as s:
+    with Solver(4, H // 2, W // 2, Cc, method=method, phi_batched=True, fused=USE_FUSED, **kw) as s:
         s.load(yq, Pq, x0=x0q, X_orig=Xq)
         s.run(iters)
         xq = torch.empty((4, H // 2, W // 2, Cc), dtype=torch.float32, device=yq.device)
@@ -248,10 +244,36 @@ def gap_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, accelerate=True, denoiser='
     pa = [float(10 * np.log10(float(H * W * Cc) / v)) for v in se.sum(axis=1)]
     xd = torch.empty((H, W, Cc), dtype=torch.float32, device=yq.device)
     check(lib.scipnp_bayer_merge(dptr(xq), dptr(xd), H, W, Cc, stream_ptr()))
-    x = xd.cpu().numpy()
+    return xd.cpu().numpy(), pa, Xo
+
+
+def gap_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, accelerate=True, denoiser='tv',
+                      iter_max=50, noise_estimate=True, sigma=None, tv_weight=0.1,
+                      tv_iter_max=5, multichannel=True, x0_bayer=None, X_orig=None,
+                      model=None, show_iqa=True):
+    """Bayer GAP-TV (pnp_sci_algo.py:20-265): the four RGGB sub-lattices are four
+    independent measurements with their own masks; the joint TV call over the
+    [H/2, W/2, 4*Cr] stack (:163-166) is per-channel, i.e. the same batch."""
+    _check_tv(denoiser, 'tv_chambolle', multichannel)
+    x, pa, Xo = _bayer_solve("gap", y_bayer, Phi_bayer, x0_bayer, X_orig, show_iqa, _total_iters(sigma, iter_max),
+                             accelerate=accelerate, _lambda=_lambda, tv_weight=tv_weight, tv_iter_max=tv_iter_max)
     _progress('GAP', pa)
     ps, ss = frames_iqa(Xo, x)
     return x, ps, ss, pa
+
+
+def admm_denoise_bayer(y_bayer, Phi_bayer, _lambda=1, gamma=0.01, denoiser='tv', iter_max=50,
+                       noise_estimate=True, sigma=None, tv_weight=0.1, tv_iter_max=5, multichannel=True,
+                       x0_bayer=None, X_orig=None, model=None, show_iqa=True):
+    """Bayer ADMM-TV (pnp_sci_algo.py:268-475).  The reference's body cannot run (``ball`` is never bound, :399);
+    this is the loop it evidently means -- ``admm_denoise`` (:805-836) on the four sub-lattices with their own
+    masks, multiplier ``ball`` starting at zero, one TV call over the [H/2, W/2, 4*Cr] stack.  Returns
+    ``(x_bayer, psnr_all)`` like :475."""
+    _check_tv(denoiser, 'tv_chambolle', multichannel)
+    x, pa, _ = _bayer_solve("admm", y_bayer, Phi_bayer, x0_bayer, X_orig, show_iqa, _total_iters(sigma, iter_max),
+                            _lambda=_lambda, gamma=gamma, tv_weight=tv_weight, tv_iter_max=tv_iter_max)
+    _progress('ADMM', pa)
+    return x, pa
 
 
 # -- R9 ------------------------------------------------------------------------
@@ -333,3 +355,55 @@ def denoise_tv_chambolle(image, weight=0.1, eps=2.e-4, n_iter_max=200, multichan
     if return_stats:
         return res, n_exec.cpu().numpy(), energy.cpu().numpy()
     return res
+
+
+# -- the stand-alone TV loops (pnp_sci_algo.py:866-907) ---------------------------
+
+def _rec_progress(tag, ni, t0, pa):
+    # the reference prints every fifth iteration (:877-881, :901-906)
+    if VERBOSE and (ni + 1) % 5 == 0 and pa:
+        print("%s: Iteration %3d, PSNR = %2.2f dB, time = %3.1fs." % (tag, ni + 1, pa[-1], time.time() - t0))
+
+
+def GAP_TV_rec(y, Phi, A, At, Phi_sum, maxiter, step_size, weight, row, col, ColT, X_ori):
+    """Accelerated GAP with ``denoise_tv_chambolle(n_iter_max=30)`` per step (pnp_sci_algo.py:866-882).  ``A`` and
+    ``At`` are the reference's two-argument mask operators and are not called: ``Phi`` is given.  The 30 dual
+    iterations run on the exact path (two launches per dual iteration, skimage's early stop on the device).
+    Returns ``f`` [row, col, ColT] (float32; the reference's loop is float64)."""
+    Phi = f32c(_host(Phi))
+    yh = f32c(_host(y))
+    if yh.shape != (row, col) or Phi.shape != (row, col, ColT):
+        raise ValueError("y / Phi do not match (row, col, ColT)")
+    Xo = None if X_ori is None else f32c(_host(X_ori))
+    t0 = time.time()
+    with Solver(1, row, col, ColT, method="gap", accelerate=True, _lambda=float(step_size),
+                tv_weight=float(weight), tv_iter_max=30, fused=USE_FUSED) as s:
+        s.load(yh[None], Phi, Phi_sum=f32c(_host(Phi_sum)), X_orig=None if Xo is None else Xo[None])
+        s.run(int(maxiter))
+        x = s.get_x()[0]
+        if VERBOSE and Xo is not None:
+            pa = [float(v) for v in s.psnr_all()[:, 0]]
+            for ni in range(int(maxiter)):
+                _rec_progress("GAP-TV", ni, t0, pa[:ni + 1])
+    return x
+
+
+def ADMM_TV_rec(y, Phi, A, At, Phi_sum, maxiter, step_size, weight, row, col, ColT, eta, X_ori):
+    """ADMM with 30 Chambolle iterations per step, TV weight x0.999 and eta x0.998 per iteration
+    (pnp_sci_algo.py:884-907).  Returns ``v``, the projection output."""
+    Phi = f32c(_host(Phi))
+    yh = f32c(_host(y))
+    if yh.shape != (row, col) or Phi.shape != (row, col, ColT):
+        raise ValueError("y / Phi do not match (row, col, ColT)")
+    Xo = None if X_ori is None else f32c(_host(X_ori))
+    weight, eta = float(weight), float(eta)
+    with Solver(1, row, col, ColT, method="admm", _lambda=float(step_size), gamma=eta,
+                tv_weight=weight, tv_iter_max=30, fused=False) as s:
+        s.load(yh[None], Phi, Phi_sum=f32c(_host(Phi_sum)), X_orig=None if Xo is None else Xo[None])
+        for ni in range(int(maxiter)):
+            s.set_tv(weight, eta)
+            s.step_async(1)
+            weight *= 0.999                      # :898
+            eta *= 0.998                         # :899
+        x = s.get_x()[0]
+    return x

@@ -746,3 +746,29 @@ def test_c_abi_kernel_entries_directly(sp):
     b2 = b.clone()
     check(lib.scipnp_admm_dual_update(ptr(b2), ptr(xo), ptr(theta), b2.numel(), st))
     assert float((b2 - (b - (xo - theta))).abs().max()) <= 1e-6
+
+
+def test_tv_rec_loops_match_the_reference(sp, golden):
+    """GAP_TV_rec / ADMM_TV_rec (pnp_sci_algo.py:866-907): 30 dual iterations per step on the exact path, ADMM with the
+    per-iteration decay of the TV weight and eta; the reference's loops are float64, the engine float32."""
+    from scipnp import pnp_sci_algo as P
+    g = golden("tv_rec")
+    H, W, Cc = g["mask"].shape
+    out = P.GAP_TV_rec(g["y"], g["mask"], None, None, g["Phi_sum"], int(g["maxiter"]), float(g["step_size"]),
+                       float(g["weight"]), H, W, Cc, g["X_orig"])
+    assert out.dtype == np.float32 and float(np.abs(out - g["gap"]).max()) <= TOL_X
+    out = P.ADMM_TV_rec(g["y"], g["mask"], None, None, g["Phi_sum"], int(g["maxiter"]), float(g["step_size"]),
+                        float(g["weight"]), H, W, Cc, float(g["eta"]), g["X_orig"])
+    assert float(np.abs(out - g["admm"]).max()) <= TOL_X
+
+
+def test_admm_denoise_bayer_matches_the_oracle(sp, path):
+    """Bayer ADMM-TV (pnp_sci_algo.py:268-475, built from admm_denoise's semantics: the reference's body is dead
+    code) against the oracle's restatement, which equals four pinned admm_denoise solves."""
+    from oracle import pnp_sci as O
+    from scipnp import synth, pnp_sci_algo as P
+    y, Phi, orig = synth.make_bayer(48, 64, 8, cfg=3)
+    kw = dict(_lambda=1, gamma=0.01, denoiser='tv', iter_max=6, tv_weight=0.1, tv_iter_max=5, X_orig=orig)
+    xo, pao = O.admm_denoise_bayer(y, Phi, **kw)
+    xg, pag = P.admm_denoise_bayer(y, Phi, **kw)
+    _cmp(xg, xo, pag, pao, path)

@@ -194,3 +194,35 @@ def test_joint_admm_multistep_and_two_period(golden):
     assert len(pa) == 4
     np.testing.assert_array_equal(x, g["x"])
     np.testing.assert_array_equal(np.array(pa), g["psnr_all"])
+
+
+def test_tv_rec_loops(golden):
+    """GAP_TV_rec / ADMM_TV_rec (pnp_sci_algo.py:866-907; float64 loops, 30 dual iterations per step) against the
+    reference's own functions (tests/golden/make_golden_rec.py)."""
+    g = golden("tv_rec")
+    H, W, Cc = g["mask"].shape
+    out = O.GAP_TV_rec(g["y"], g["mask"], O.A_, O.At_, g["Phi_sum"], int(g["maxiter"]), float(g["step_size"]),
+                       float(g["weight"]), H, W, Cc, g["X_orig"])
+    assert out.dtype == np.float64
+    np.testing.assert_array_equal(out, g["gap"])
+    out = O.ADMM_TV_rec(g["y"], g["mask"], O.A_, O.At_, g["Phi_sum"], int(g["maxiter"]), float(g["step_size"]),
+                        float(g["weight"]), H, W, Cc, float(g["eta"]), g["X_orig"])
+    np.testing.assert_array_equal(out, g["admm"])
+
+
+def test_admm_denoise_bayer_is_four_pinned_admm_solves():
+    """admm_denoise_bayer (pnp_sci_algo.py:268-475) is dead code in the reference (NameError at :399), so its
+    restatement cannot be pinned directly; it must equal the pinned admm_denoise (R5) run on each sub-lattice."""
+    rng = np.random.default_rng(5)
+    Phi = (rng.random((24, 28, 4)) <= 0.5).astype(np.float32)
+    orig = rng.random((24, 28, 4), dtype=np.float32)
+    y = np.sum(Phi * orig, axis=2)
+    x, pa = O.admm_denoise_bayer(y, Phi, _lambda=1, gamma=0.02, denoiser='tv', iter_max=5, tv_weight=0.2,
+                                 tv_iter_max=4, X_orig=orig)
+    assert len(pa) == 5
+    for (i, j) in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        P = np.ascontiguousarray(Phi[i::2, j::2])
+        A, At = _ops(P)
+        xs = O.admm_denoise(np.ascontiguousarray(y[i::2, j::2]), O.phi_sum(P), A, At, _lambda=1, gamma=0.02,
+                            iter_max=5, tv_weight=0.2, tv_iter_max=4)[0]
+        np.testing.assert_array_equal(x[i::2, j::2], xs)
