@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["partition_rows", "exchange_halos", "TiledSolver", "tiled_reference_run"]
+__all__ = ["partition_rows", "exchange_halos", "TiledSolver", "tiled_reference_run", "gap_denoise_tiled"]
 
 
 def partition_rows(H, world, rank, halo):
@@ -405,3 +405,44 @@ def tiled_reference_run(step_fn, fields, H, halo, k, iters, rank, world, group=N
             step_fn()
         done += n
         exchange_halos(fields(), H, halo, rank, world, group)
+
+
+def gap_denoise_tiled(y, Phi_sum=None, A=None, At=None, _lambda=1, accelerate=True, denoiser='tv', iter_max=50,
+                      noise_estimate=False, sigma=None, tv_weight=0.1, tv_iter_max=5, multichannel=True, x0=None,
+                      X_orig=None, model=None, show_iqa=True, tvm='tv_chambolle', Phi=None, group=None,
+                      exchange_every=1, transport="auto"):
+    """``gap_denoise`` (pnp_sci_algo.py:536-706) for ONE scene over all ranks of ``group``: the one-call entry of the
+    row-tiled mode.  Every rank calls it with the same whole-scene arguments (host arrays, the reference's
+    signature plus ``Phi=``); the function slices this rank's rows, runs the tiled solver and gathers the owned
+    rows, so every rank returns the complete ``(x, psnr_, ssim_, psnr_all)``.  ``psnr_all`` (the per-iteration
+    track) is not kept in tiled mode and comes back empty; ``Phi_sum`` is recomputed on the device."""
+    from .pnp_sci_algo import _check_tv, _recover_phi, _host, _total_iters
+    from .engine import f32c
+    from .iqa import frames_iqa
+    _check_tv(denoiser, tvm, multichannel)
+    Phi = _recover_phi(A, At, y, Phi)
+    yh = f32c(_host(y))
+    H, W, Cc = Phi.shape
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    ts = TiledSolver(H, W, Cc, rank, world, tv_weight=tv_weight, tv_iter_max=tv_iter_max, _lambda=_lambda,
+                     accelerate=accelerate, exchange_every=exchange_every, group=group, transport=transport)
+    try:
+        a, b = ts.row_lo, ts.row_hi
+        dev = ts.device
+        ts.load(torch.from_numpy(yh[a:b]).to(dev), torch.from_numpy(Phi[a:b]).to(dev),
+                None if x0 is None else torch.from_numpy(f32c(_host(x0))[a:b]).to(dev))
+        ts.run(_total_iters(sigma, iter_max))
+        mine = ts.owned().cpu().numpy()
+        lo = ts.lo
+    finally:
+        ts.close()
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, (lo, mine), group=group)
+        x = np.concatenate([p[1] for p in sorted(parts, key=lambda t: t[0])], axis=0)
+    else:
+        x = mine
+    Xo = None if X_orig is None else f32c(_host(X_orig))
+    ps, ss = frames_iqa(Xo, x)
+    return x, ps, ss, []

@@ -191,3 +191,44 @@ def test_p2p_tiled_stopping_rule_sums_energies_over_all_ranks(sp, tmp_path):
     full, _ = _single(H, W, C, iters, fused=False, tv_eps=0.0, T=20)
     assert float(np.abs(ref - full).max()) > 1e-4, "the stopping rule never fired: the test would be vacuous"
     assert float(np.abs(got - ref).max()) <= 1e-6
+
+
+def _onecall_worker(rank, world, port, H, W, C, iters, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from scipnp.tiled import gap_denoise_tiled
+        from scipnp import synth
+        meas, mask, orig = synth.make_cacti(H, W, C, 1, cfg=21)
+        y = meas[:, :, 0] / np.float32(255.)
+        x, ps, ss, pa = gap_denoise_tiled(y, None, Phi=mask, iter_max=iters, tv_weight=0.3, tv_iter_max=5,
+                                          X_orig=orig[:, :, :C] / np.float32(255.), transport="p2p")
+        np.save(os.path.join(out_dir, "one_%d.npy" % rank), x)
+        np.save(os.path.join(out_dir, "one_ps_%d.npy" % rank), np.array(ps))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gap_denoise_tiled_one_call_entry(sp, tmp_path):
+    """The reference's gap_denoise signature over two ranks: every rank passes the whole scene and gets the whole
+    reconstruction back, equal to the single-GPU gap_denoise."""
+    import socket
+    import torch.multiprocessing as mp
+    H, W, C, iters = 72, 128, 8, 6
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_onecall_worker, args=(2, port, H, W, C, iters, str(tmp_path)), nprocs=2, join=True)
+    from scipnp import synth
+    meas, mask, orig = synth.make_cacti(H, W, C, 1, cfg=21)
+    y = meas[:, :, 0] / np.float32(255.)
+    ms = mask.sum(axis=2)
+    ms[ms == 0] = 1
+    ref, ps, _, _ = sp.gap_denoise(y, ms, Phi=mask, iter_max=iters, tv_weight=0.3, tv_iter_max=5,
+                                   X_orig=orig[:, :, :C] / np.float32(255.))
+    for r in range(2):
+        x = np.load(tmp_path / ("one_%d.npy" % r))
+        assert x.shape == (H, W, C) and float(np.abs(x - ref).max()) <= 1e-6
+        assert np.abs(np.load(tmp_path / ("one_ps_%d.npy" % r)) - np.array(ps)).max() <= 1e-3
