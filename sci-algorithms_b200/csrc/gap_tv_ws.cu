@@ -167,6 +167,9 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
         if (const char* e = getenv("SCIPNP_WS_EDGE")) { int v = atoi(e); if (v >= 0 && v <= 16) w = v; }
         const int ngr = (a.W + own - 1) / own, nst = (ngr + ws_groups(Q) - 1) / ws_groups(Q);
         p.edge_cost = nst > 2 ? w : 0;
+        // rows of one CTA's share: programmatic dependent launch pays below about a hundred
+        const long long per = (long long)a.B * nst * (p.out_hi - p.out_lo + p.seg_cost) / (grid > 0 ? grid : 1);
+        p.use_pdl = per < 96 ? 1 : 0;
     }
     p.own = own;
     p.ngroups = (a.W + own - 1) / own;
