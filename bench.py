@@ -388,12 +388,12 @@ def run_ours(args):
         solver = TiledSolver(H, W, CR, rank, world, tv_weight=TV_WEIGHT, tv_iter_max=TV_ITER,
                              exchange_every=args.exchange_every, transport=args.transport)
         y, Phi, _ = device_scene(torch, solver.local_rows, W, CR, row0=solver.row_lo)
-        load = lambda: solver.load(y, Phi)
+        load = lambda: solver.load(y, Phi, borrow_phi=True)
     else:
         solver = Solver(1, H, W, CR, method="gap", accelerate=True, _lambda=1.0,
                         tv_weight=TV_WEIGHT, tv_iter_max=TV_ITER)
         y, Phi, _ = device_scene(torch, H, W, CR)
-        load = lambda: solver.load(y[None], Phi)
+        load = lambda: solver.load(y[None], Phi, borrow_phi=True)
 
     def step():
         load()
@@ -550,6 +550,9 @@ def run_ours(args):
         "config": {"workload": "c5 GAP-TV 3840x2160xCr=24 CACTI, lambda=1, accelerated, "
                                "tv_weight=0.3, tv_iter_max=5", "iters_per_step": iters,
                    "l2": "state per iteration (2.5 GB) exceeds the 126 MB L2; no flush needed",
+                   "inputs": "y and the mask stack resident in HBM; a step = load (y copied into the solver, the "
+                             "masks read in place, Phi_sum and x0 = At(y) in one pass) + %d iterations + the "
+                             "early-stop decision" % iters,
                    "path": "fused" if fused else "exact", "refined_iters": refined,
                    "parallelism": ("row-tiled x%d, %d halo rows, neighbour exchange every %d iteration(s)"
                                    % (world, 4 * args.exchange_every, args.exchange_every)) if world > 1 else "single GPU",

@@ -201,6 +201,12 @@ int scipnp_solver_load(scipnp_solver *s, const float *y, const float *Phi,
  * is the sheared canvas width; `mask2d` is the coded aperture [H][W-(C-1)*step] (host or device).
  * The fused iterations read the aperture at per-band index offsets, Phi[h,w,c] = M[h, w-step*c],
  * instead of streaming a shifted mask stack from HBM.                                       */
+/* scipnp_solver_load with the mask stack BORROWED: `Phi_dev` (device memory, 16-byte aligned) is read in place by
+ * every iteration instead of being copied into the handle; it must stay valid and unchanged until the results were
+ * read.  Saves one pass over the mask stack per reconstruction (the masks of a CACTI camera are constant over the
+ * frame loop, pnp_sci_algo.py:498-529). */
+int scipnp_solver_load_borrow_phi(scipnp_solver *s, const float *y, const float *Phi_dev, const float *Phi_sum,
+                                  const float *x0, const float *X_orig, void *stream);
 int scipnp_solver_load_cassi(scipnp_solver *s, const float *y, const float *mask2d, int step,
                              const float *x0, const float *X_orig, void *stream);
 

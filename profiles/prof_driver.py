@@ -29,7 +29,8 @@ orig = 0.45 + 0.25 * torch.sin((xx + 3. * tt + 5. * bb) / 37.) * torch.cos(yy / 
 y = (Phi * orig).sum(3)
 tv_eps = float(os.environ.get("TV_EPS", "2e-4"))      # TV_EPS=0: timing experiments whose results are not meaningful
 s = Solver(B, H, W, C, method=method, tv_weight=0.3, tv_iter_max=5, fused=bool(fused), tv_eps=tv_eps, phi_batched=B > 1)
-s.load(y, Phi if B > 1 else Phi[0])
+Pin = Phi if B > 1 else Phi[0].contiguous()
+s.load(y, Pin, borrow_phi=bool(int(os.environ.get('BORROW', '0'))))
 s.run(iters)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -13,6 +13,9 @@ int launch_project(int mode, const float* a_in, const float* b_in, float* x_out,
                    int phi_batched, cudaStream_t st);
 
 int launch_clip01(float* x, size_t n, cudaStream_t st);
+// Phi_sum and x0 = At(y) in one pass over the mask stack; SCIPNP_EINVAL (nothing launched) if the shape is not covered
+int launch_init_x0_phisum(const float* y, const float* Phi, float* x, float* phisum, int B, int H, int W, int C,
+                          int phi_batched, cudaStream_t st);
 int launch_sq_err(const float* a, const float* b, size_t n_per_batch, int B, double* sums,
                   cudaStream_t st);
 

@@ -110,6 +110,37 @@ __global__ void At_kernel_v4(const float* __restrict__ y, const float4* __restri
     x[(size_t)b * nelem4 + e] = make_float4(__fmul_rn(yv, m.x), __fmul_rn(yv, m.y), __fmul_rn(yv, m.z), __fmul_rn(yv, m.w));
 }
 
+// Start of a reconstruction in one pass over the mask stack: Phi_sum (mask_sum, pnp_sci_algo.py:491-492, NumPy's
+// summation order) and the default initial guess x0 = At(y) (pnp_sci_algo.py:621-622).  A CTA owns kInitP consecutive
+// pixels: coalesced 128-bit loads of Phi, x0 written straight from the loaded registers, the masks parked in shared
+// memory (row stride C+1: conflict-free) for the one-thread-per-pixel sum.
+constexpr int kInitP = 64, kInitThreads = 256;
+__global__ void __launch_bounds__(kInitThreads)
+init_x0_phisum_kernel(const float* __restrict__ y, const float4* __restrict__ Phi, float4* __restrict__ x,
+                      float* __restrict__ phisum, long long npix, int C4, long long phi_stride4, int phisum_batched) {
+    extern __shared__ float sm_init[];
+    const int b = blockIdx.y, C = 4 * C4, ld = C + 1;
+    const long long p0 = (long long)blockIdx.x * kInitP;
+    const int n = (int)((npix - p0) < kInitP ? (npix - p0) : kInitP);
+    const float4* src = Phi + (size_t)b * phi_stride4 + (size_t)p0 * C4;
+    float4* dst = x + ((size_t)b * npix + p0) * C4;
+    const float* yb = y + (size_t)b * npix + p0;
+    for (int i = threadIdx.x; i < n * C4; i += kInitThreads) {
+        const float4 m = src[i];
+        const int px = i / C4, k = i - px * C4;
+        const float yv = yb[px];
+        dst[i] = make_float4(__fmul_rn(yv, m.x), __fmul_rn(yv, m.y), __fmul_rn(yv, m.z), __fmul_rn(yv, m.w));
+        float* r = sm_init + px * ld + 4 * k;
+        r[0] = m.x; r[1] = m.y; r[2] = m.z; r[3] = m.w;
+    }
+    if (!phisum_batched && b != 0) return;            // one Phi_sum for all measurements: the first slice writes it
+    __syncthreads();
+    if ((int)threadIdx.x < n) {
+        const float acc = numpy_sum(sm_init + threadIdx.x * ld, C, 1);
+        phisum[(size_t)(phisum_batched ? b : 0) * npix + p0 + threadIdx.x] = (acc == 0.f) ? 1.f : acc;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // R4 / R5 projection, coalesced: a CTA owns P consecutive pixels; products go
 // through shared memory (transposed, [C][P]) so that one thread per pixel can
@@ -354,6 +385,22 @@ int launch_sq_err(const float* a, const float* b, size_t n_per_batch, int B, dou
 }  // namespace scipnp
 
 using namespace scipnp;
+
+// x0 = At(y) and Phi_sum in one pass (internal; see init_x0_phisum_kernel).  Returns SCIPNP_EINVAL without launching
+// when the shape is not covered (the caller then uses scipnp_phi_sum + scipnp_At).
+namespace scipnp {
+int launch_init_x0_phisum(const float* y, const float* Phi, float* x, float* phisum, int B, int H, int W, int C,
+                          int phi_batched, cudaStream_t st) {
+    if ((C & 3) != 0 || C > kMaxLocalC || !aligned16(Phi) || !aligned16(x)) return SCIPNP_EINVAL;
+    const long long npix = (long long)H * W;
+    dim3 grid((unsigned)ceil_div_ll(npix, kInitP), B);
+    const size_t smem = (size_t)kInitP * (C + 1) * sizeof(float);
+    init_x0_phisum_kernel<<<grid, kInitThreads, smem, st>>>(y, reinterpret_cast<const float4*>(Phi), reinterpret_cast<float4*>(x),
+                                                           phisum, npix, C / 4, phi_batched ? npix * (C / 4) : 0, phi_batched ? 1 : 0);
+    count_launch();
+    return check_launch("init_x0_phisum_kernel");
+}
+}  // namespace scipnp
 
 extern "C" {
 

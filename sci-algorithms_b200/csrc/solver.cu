@@ -36,6 +36,8 @@ struct scipnp_solver {
     float *ba = nullptr, *bb = nullptr;       // ADMM multiplier ping-pong
     float *xproj = nullptr, *fbuf = nullptr;  // ADMM x and TV input
     float *y = nullptr, *Phi = nullptr, *PhiSum = nullptr, *Xorig = nullptr;
+    const float* phi = nullptr;               // the mask stack the iterations read: Phi (owned copy) or the caller's array
+    bool sqerr_dirty = true;                  // the squared-error track holds values of an earlier reconstruction
     float *xsnap = nullptr, *y1snap = nullptr, *bsnap = nullptr;   // rollback copies (fused)
     void* tvws = nullptr; size_t tvws_bytes = 0;
     void* fws = nullptr; size_t fws_bytes = 0; bool fws_clean = false;
@@ -171,24 +173,39 @@ static int ensure_exact_buffers(scipnp_solver* s) {
     return SCIPNP_OK;
 }
 
-int scipnp_solver_load(scipnp_solver* s, const float* y, const float* Phi, const float* Phi_sum,
-                       const float* x0, const float* X_orig, void* stream) {
+static int solver_load(scipnp_solver* s, const float* y, const float* Phi, const float* Phi_sum,
+                       const float* x0, const float* X_orig, bool borrow_phi, void* stream) {
     SCIPNP_REQUIRE(s && y && Phi, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const scipnp_params& p = s->p;
     s->cassi = false;
     SCIPNP_CUDA(cudaMemcpyAsync(s->y, y, s->n_meas * sizeof(float), cudaMemcpyDefault, st));
-    if (Phi != s->Phi) SCIPNP_CUDA(cudaMemcpyAsync(s->Phi, Phi, s->n_phi * sizeof(float), cudaMemcpyDefault, st));
-    if (Phi_sum) {
-        SCIPNP_CUDA(cudaMemcpyAsync(s->PhiSum, Phi_sum, s->n_phisum * sizeof(float), cudaMemcpyDefault, st));
+    if (borrow_phi) {
+        // the caller's device array is read in place for the whole reconstruction (it must stay valid and
+        // unchanged until the results were read); saves one pass over the mask stack per reconstruction
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, Phi) != cudaSuccess || at.type != cudaMemoryTypeDevice || !aligned16(Phi)) {
+            cudaGetLastError();
+            set_error("borrowed Phi must be 16-byte aligned device memory");
+            return SCIPNP_EINVAL;
+        }
+        s->phi = Phi;
     } else {
-        if (int e = scipnp_phi_sum(s->Phi, s->PhiSum, p.phi_batched ? p.B : 1, p.H, p.W, p.C, stream)) return e;
+        if (Phi != s->Phi) SCIPNP_CUDA(cudaMemcpyAsync(s->Phi, Phi, s->n_phi * sizeof(float), cudaMemcpyDefault, st));
+        s->phi = s->Phi;
     }
-    if (x0) {
-        SCIPNP_CUDA(cudaMemcpyAsync(s->xa, x0, s->n_frame * sizeof(float), cudaMemcpyDefault, st));
-    } else {
-        if (int e = scipnp_At(s->y, s->Phi, s->xa, p.B, p.H, p.W, p.C, p.phi_batched, stream)) return e;
+    bool need_sum = Phi_sum == nullptr, need_x0 = x0 == nullptr;
+    if (Phi_sum) SCIPNP_CUDA(cudaMemcpyAsync(s->PhiSum, Phi_sum, s->n_phisum * sizeof(float), cudaMemcpyDefault, st));
+    if (x0) SCIPNP_CUDA(cudaMemcpyAsync(s->xa, x0, s->n_frame * sizeof(float), cudaMemcpyDefault, st));
+    if (need_sum && need_x0) {           // both in one pass over the masks where the shape allows it
+        const int e = launch_init_x0_phisum(s->y, s->phi, s->xa, s->PhiSum, p.B, p.H, p.W, p.C, p.phi_batched, st);
+        if (e == SCIPNP_OK) need_sum = need_x0 = false;
+        else if (e != SCIPNP_EINVAL) return e;
     }
+    if (need_sum)
+        if (int e = scipnp_phi_sum(s->phi, s->PhiSum, p.phi_batched ? p.B : 1, p.H, p.W, p.C, stream)) return e;
+    if (need_x0)
+        if (int e = scipnp_At(s->y, s->phi, s->xa, p.B, p.H, p.W, p.C, p.phi_batched, stream)) return e;
     s->x0_given = x0 != nullptr;
     s->has_orig = X_orig != nullptr;
     if (X_orig) SCIPNP_CUDA(cudaMemcpyAsync(s->Xorig, X_orig, s->n_frame * sizeof(float), cudaMemcpyDefault, st));
@@ -199,12 +216,25 @@ int scipnp_solver_load(scipnp_solver* s, const float* y, const float* Phi, const
         // x = x0 until the first projection (pnp_sci_algo.py:800)
         SCIPNP_CUDA(cudaMemcpyAsync(s->xproj, s->xa, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
-    SCIPNP_CUDA(cudaMemsetAsync(s->sqerr, 0, kPsnrCap * sizeof(double), st));
+    if (s->has_orig || s->sqerr_dirty) SCIPNP_CUDA(cudaMemsetAsync(s->sqerr, 0, kPsnrCap * sizeof(double), st));
+    s->sqerr_dirty = s->has_orig;
     s->loaded = true;
     s->iters_done = 0;
     s->psnr_count = 0;
     s->refined = 0;
     return SCIPNP_OK;
+}
+
+int scipnp_solver_load(scipnp_solver* s, const float* y, const float* Phi, const float* Phi_sum,
+                       const float* x0, const float* X_orig, void* stream) {
+    return solver_load(s, y, Phi, Phi_sum, x0, X_orig, false, stream);
+}
+
+// The same with the mask stack BORROWED: `Phi_dev` (device memory, 16-byte aligned) is read in place by every
+// iteration instead of being copied into the handle; it must stay valid and unchanged until the results were read.
+int scipnp_solver_load_borrow_phi(scipnp_solver* s, const float* y, const float* Phi_dev, const float* Phi_sum,
+                                  const float* x0, const float* X_orig, void* stream) {
+    return solver_load(s, y, Phi_dev, Phi_sum, x0, X_orig, true, stream);
 }
 
 // R9: CASSI.  `mask2d` is the coded aperture [H][W-(C-1)*step]; the solver's W is the sheared canvas.
@@ -242,7 +272,7 @@ static int step_exact(scipnp_solver* s, int k, cudaStream_t st) {
     const scipnp_params& p = s->p;
     if (p.method == 0) {
         int mode = p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN;
-        if (int e = launch_project(mode, s->xa, nullptr, s->xa, nullptr, s->y1a, s->y1a, s->y, s->Phi,
+        if (int e = launch_project(mode, s->xa, nullptr, s->xa, nullptr, s->y1a, s->y1a, s->y, s->phi,
                                    s->PhiSum, p.lambda, 0.f, p.B, p.H, p.W, p.C, p.phi_batched, st)) return e;
         if (int e = tv_chambolle_exact(s->xa, s->xb, p.tv_weight, p.tv_eps, p.tv_iter_max, p.B, p.H, p.W,
                                        p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st,
@@ -252,7 +282,7 @@ static int step_exact(scipnp_solver* s, int k, cudaStream_t st) {
         if (int e = record_sqerr(s, k, s->xa, st)) return e;
     } else {
         if (int e = launch_project(MODE_ADMM, s->xa, s->ba, s->xproj, s->fbuf, nullptr, nullptr, s->y,
-                                   s->Phi, s->PhiSum, p.lambda, p.gamma, p.B, p.H, p.W, p.C,
+                                   s->phi, s->PhiSum, p.lambda, p.gamma, p.B, p.H, p.W, p.C,
                                    p.phi_batched, st)) return e;
         if (int e = tv_chambolle_exact(s->fbuf, s->xa, p.tv_weight, p.tv_eps, p.tv_iter_max, p.B, p.H,
                                        p.W, p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st)) return e;
@@ -267,7 +297,7 @@ static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
     const scipnp_params& p = s->p;
     FusedArgs a{};
     a.x_in = s->xa; a.x_out = s->xb;
-    a.y = s->y; a.Phi = s->Phi; a.Phi_sum = s->PhiSum;
+    a.y = s->y; a.Phi = s->phi; a.Phi_sum = s->PhiSum;
     if (s->cassi) { a.Phi = nullptr; a.mask2d = s->mask2d; a.cassi_step = s->cassi_step; a.mask_w = s->mask_w; }
     a.lambda = p.lambda; a.gamma = p.gamma;
     a.tv_weight = p.tv_weight; a.tv_eps = p.tv_eps; a.tv_iter_max = p.tv_iter_max;
@@ -383,7 +413,7 @@ int scipnp_solver_rollback(scipnp_solver* s, void* stream) {
         if (p.method == 0) SCIPNP_CUDA(cudaMemcpyAsync(s->y1a, s->y1snap, s->n_meas * sizeof(float), cudaMemcpyDeviceToDevice, st));
         else SCIPNP_CUDA(cudaMemcpyAsync(s->ba, s->bsnap, s->n_frame * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {                                   // the load state (scipnp_solver_load)
-        if (int e = scipnp_At(s->y, s->Phi, s->xa, p.B, p.H, p.W, p.C, p.phi_batched, stream)) return e;
+        if (int e = scipnp_At(s->y, s->phi, s->xa, p.B, p.H, p.W, p.C, p.phi_batched, stream)) return e;
         if (p.method == 0) {
             SCIPNP_CUDA(cudaMemsetAsync(s->y1a, 0, s->n_meas * sizeof(float), st));
         } else {

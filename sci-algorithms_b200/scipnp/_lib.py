@@ -75,6 +75,7 @@ _SIGS = {
     "scipnp_solver_create": (C.c_int, [C.POINTER(Params), C.POINTER(_vp)]),
     "scipnp_solver_destroy": (C.c_int, [_vp]),
     "scipnp_solver_load": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _vp]),
+    "scipnp_solver_load_borrow_phi": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "scipnp_solver_load_cassi": (C.c_int, [_vp, _fp, _fp, _i, _fp, _fp, _vp]),
     "scipnp_solver_run": (C.c_int, [_vp, _i, _vp]),
     "scipnp_solver_begin": (C.c_int, [_vp, _vp]),

@@ -220,7 +220,10 @@ class Solver:
         self._keep.append(a)
         return a
 
-    def load(self, y, Phi, Phi_sum=None, x0=None, X_orig=None):
+    def load(self, y, Phi, Phi_sum=None, x0=None, X_orig=None, borrow_phi=False):
+        """Inputs of one reconstruction (host arrays or device tensors).  ``borrow_phi=True`` with a device tensor:
+        the mask stack is read in place by every iteration instead of being copied into the handle (it must not
+        change until the results were read; the handle keeps a reference)."""
         B, H, W, Cc = self.shape
         pb = self.params.phi_batched
         self._keep = []
@@ -229,8 +232,10 @@ class Solver:
         Phi_sum = self._chk(Phi_sum, (B, H, W) if pb else (H, W), "Phi_sum")
         x0 = self._chk(x0, (B, H, W, Cc), "x0")
         X_orig = self._chk(X_orig, (B, H, W, Cc), "X_orig")
-        check(lib.scipnp_solver_load(self._h, dptr(y), dptr(Phi), dptr(Phi_sum), dptr(x0),
-                                     dptr(X_orig), stream_ptr()))
+        borrow = bool(borrow_phi) and is_torch(Phi) and Phi.is_cuda
+        fn = lib.scipnp_solver_load_borrow_phi if borrow else lib.scipnp_solver_load
+        check(fn(self._h, dptr(y), dptr(Phi), dptr(Phi_sum), dptr(x0), dptr(X_orig), stream_ptr()))
+        self._phi_ref = Phi if borrow else None
         if any(not is_torch(a) for a in self._keep):
             torch.cuda.current_stream().synchronize()   # pageable host sources
         self._keep = []

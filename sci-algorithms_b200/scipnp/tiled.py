@@ -187,11 +187,12 @@ class TiledSolver:
                 raise RuntimeError("halo push could be set up on some ranks only")
 
     # -- data ----------------------------------------------------------------------------
-    def load(self, y_local, Phi_local, x0_local=None, X_orig_local=None):
-        """Inputs restricted to rows [row_lo, row_hi) (device tensors or host arrays)."""
+    def load(self, y_local, Phi_local, x0_local=None, X_orig_local=None, borrow_phi=False):
+        """Inputs restricted to rows [row_lo, row_hi) (device tensors or host arrays); ``borrow_phi`` as in
+        ``Solver.load``."""
         self.solver.load(y_local[None], Phi_local,
                          x0=None if x0_local is None else x0_local[None],
-                         X_orig=None if X_orig_local is None else X_orig_local[None])
+                         X_orig=None if X_orig_local is None else X_orig_local[None], borrow_phi=borrow_phi)
 
     def _fields(self):
         xp, y1p = self.solver.state_ptrs()
