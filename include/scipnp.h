@@ -112,6 +112,18 @@ int scipnp_tv_chambolle_fused(const float *in, float *out, double weight, double
  *     the 'ATV_ClipA' branch of gapdenoise.m:93-94): anisotropic TV by iterative clipping,
  *     alpha = 5, per 2-D frame of a [B][H][W][C] stack; `iters` iterations, the x of the last one
  *     is returned.  workspace: scipnp_tv_atv_clip_workspace_bytes (the two dual fields).       */
+/* The rest of the MATLAB twin's TV family (gapdenoise.m:86-108) on [B][H][W][C] stacks, C = the frames (<= 128):
+ *   variant 0  ATV_ClipB   TV_denoising_clip_LB.m:25-36      lambda = tvweight
+ *           1  ATV_cham    tvdenoise_cham_ATV2D.m:72-87      lambda = 1/tvweight (as gapdenoise.m:98 passes it)
+ *           2  ITV2D_cham  tvdenoise_cham_ITV2D.m:73-90      lambda = 1/tvweight
+ *           3  ITV3D_cham  tvdenoise_cham_ITV3D.m:72-90      lambda = 1/tvweight
+ *           4  ATV_FGP     fgp_denoise_ATV2D.m:73-121        lambda = tvweight, iters = MAXITER
+ *           5  ITV2D_FGP   fgp_denoise_ITV2D.m:73-121
+ *           6  ITV3D_FGP   fgp_denoise_ITV3D.m:73-121
+ * IEEE single precision in the statement order of the .m files.  workspace: scipnp_tv_matlab_workspace_bytes.  */
+size_t scipnp_tv_matlab_workspace_bytes(int B, int H, int W, int C);
+int scipnp_tv_matlab(const float *in, float *out, int variant, float lambda, int iters, int B, int H, int W, int C,
+                     void *workspace, size_t workspace_bytes, void *stream);
 size_t scipnp_tv_atv_clip_workspace_bytes(int B, int H, int W, int C);
 int scipnp_tv_atv_clip(const float *in, float *out, float lambda, int iters, int B, int H, int W,
                        int C, void *workspace, size_t workspace_bytes, void *stream);

@@ -10,7 +10,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr"
 if [ -n "$SCIPNP_FAST" ]; then FLAGS="$FLAGS -DSCIPNP_FUSED_FAST_BUILD"; fi
 mkdir -p "$HERE/build"
-UNITS="api ops tv_exact gap_tv_fused fused_inst_r2 fused_inst_r3 fused_inst_r4 fused_inst_r4c gap_tv_ws ws_inst_r2 ws_inst_r3 ws_inst_r4 solver"
+UNITS="api ops tv_exact tv_matlab gap_tv_fused fused_inst_r2 fused_inst_r3 fused_inst_r4 fused_inst_r4c gap_tv_ws ws_inst_r2 ws_inst_r3 ws_inst_r4 solver"
 OBJS=""
 PIDS=""
 STAMP="$HERE/build/.flags"

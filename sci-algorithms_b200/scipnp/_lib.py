@@ -60,6 +60,8 @@ _SIGS = {
     "scipnp_tv_fused_supported": (C.c_int, [_i, _i, _i, _i, _i]),
     "scipnp_tv_chambolle_fused": (C.c_int, [_fp, _fp, C.c_double, C.c_double, _i, _i, _i, _i, _i,
                                             _vp, C.c_size_t, _vp, _vp]),
+    "scipnp_tv_matlab_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "scipnp_tv_matlab": (C.c_int, [_fp, _fp, _i, C.c_float, _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "scipnp_tv_atv_clip_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "scipnp_tv_atv_clip": (C.c_int, [_fp, _fp, C.c_float, _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "scipnp_sq_err": (C.c_int, [_fp, _fp, C.c_size_t, _vp, _vp]),

@@ -660,7 +660,7 @@ def test_matlab_gapdenoise_loop(sp, golden):
         assert np.abs(got - v).max() <= TOL_EXACT
         assert np.abs(np.array(pa) - np.array(want_psnr)).max() <= TOL_DB
     with pytest.raises(ValueError):
-        G.gapdenoise(y, mask, tvm='ITV2D_cham', maxiter=1)
+        G.gapdenoise(y, mask, tvm='no_such_tv', maxiter=1)
 
 
 def test_data_side_on_device(sp):
@@ -801,3 +801,48 @@ def test_load_one_pass_init_and_borrowed_masks(sp, B, H, W, Cc, pb):
     ref = Phi[0].sum(axis=2) if pb else Phi.sum(axis=2)
     ref[ref == 0] = 1
     np.testing.assert_array_equal(np.asarray(ms), ref)
+
+
+_FAMILY = [("TV_denoising_clip_LB", 0.07, 5), ("tvdenoise_cham_ATV2D", 1 / 0.07, 5), ("tvdenoise_cham_ITV2D", 1 / 0.07, 5),
+           ("tvdenoise_cham_ITV3D", 1 / 0.07, 5), ("fgp_denoise_ATV2D", 0.07, 2), ("fgp_denoise_ITV2D", 0.07, 4),
+           ("fgp_denoise_ITV3D", 0.07, 3)]
+
+
+@pytest.mark.parametrize("name,lam,iters", _FAMILY)
+@pytest.mark.parametrize("shape", [(24, 20, 8), (17, 23, 5), (9, 12, 24)])
+def test_matlab_tv_family_bit_exact(sp, name, lam, iters, shape):
+    """the rest of the MATLAB twin's TV family (gapdenoise.m:86-108) against the float32 NumPy
+    restatement of the .m files (oracle/matlab_tv.py; parity unpinned: no MATLAB here), statement order kept."""
+    from oracle import matlab_tv as M
+    from scipnp import matlab_tv as G
+    rng = np.random.default_rng(17)
+    y = rng.random(shape, dtype=np.float32)
+    got = getattr(G, name)(y, lam, iters)
+    want = getattr(M, name)(y, lam, iters)
+    assert got.dtype == np.float32 and want.dtype == np.float32
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("tvm", ["ATV_ClipB", "ATV_cham", "ATV_FGP", "ITV2D_cham", "ITV2D_FGP", "ITV3D_cham", "ITV3D_FGP"])
+def test_matlab_gapdenoise_tvm_switch(sp, golden, tvm):
+    """gapdenoise.m:92-108: every `tvm` branch with the weight and the iteration count as written there."""
+    from oracle import matlab_tv as M
+    from oracle import pnp_sci as O
+    from scipnp import matlab_tv as G
+    g = golden("gap_acc")
+    mask, y = g["mask"], g["y"]
+    Phisum = np.sum(mask * mask, axis=2)
+    Phisum[Phisum == 0] = 1
+    w = 0.07
+    tv = {"ATV_ClipB": lambda v: M.TV_denoising_clip_LB(v, w, 5), "ATV_cham": lambda v: M.tvdenoise_cham_ATV2D(v, 1 / w, 5),
+          "ATV_FGP": lambda v: M.fgp_denoise_ATV2D(v, w, 2), "ITV2D_cham": lambda v: M.tvdenoise_cham_ITV2D(v, 1 / w, 5),
+          "ITV2D_FGP": lambda v: M.fgp_denoise_ITV2D(v, w, 2), "ITV3D_cham": lambda v: M.tvdenoise_cham_ITV3D(v, 1 / w, 5),
+          "ITV3D_FGP": lambda v: M.fgp_denoise_ITV3D(v, w, 2)}[tvm]
+    v = O.At_(y, mask)
+    y1 = np.zeros_like(y)
+    for _ in range(4):
+        yb = O.A_(v, mask)
+        y1 = y1 + (y - yb)
+        v = tv(v + np.float32(0.2) * O.At_((y1 - yb) / Phisum, mask))
+    got, _ = G.gapdenoise(y, mask, lambda_=0.2, maxiter=4, acc=True, tvweight=w, tvm=tvm)
+    assert np.abs(got - v).max() <= TOL_EXACT

@@ -141,3 +141,55 @@ def test_matlab_tv_keeps_single_precision():
     assert M.TV_denoising(y, 0.1, 5).dtype == np.float32
     with pytest.raises(ValueError):
         M.TV_denoising(y[:1], 0.1, 5)
+
+
+# -- the rest of the MATLAB TV family (oracle/matlab_tv.py; parity unpinned: checked by properties) ----------------
+
+_FAMILY = ["TV_denoising_clip_LB", "tvdenoise_cham_ATV2D", "tvdenoise_cham_ITV2D", "tvdenoise_cham_ITV3D",
+           "fgp_denoise_ATV2D", "fgp_denoise_ITV2D", "fgp_denoise_ITV3D"]
+
+
+def _lam(name):
+    return 12.0 if "cham" in name else 0.08        # the Chambolle variants take 1/weight (gapdenoise.m:98)
+
+
+@pytest.mark.parametrize("name", _FAMILY)
+def test_matlab_family_properties(name):
+    from oracle import matlab_tv as M
+    fn = getattr(M, name)
+    y = _frames((18, 22, 4))
+    u = fn(y, _lam(name), 4)
+    assert u.dtype == np.float32 and u.shape == y.shape
+    # a constant stack is a fixed point
+    c = np.full((8, 9, 3), 0.4, np.float32)
+    np.testing.assert_allclose(fn(c, _lam(name), 3), c, atol=1e-6)
+    # denoising reduces the total variation of the frames
+    tv = lambda a: float(np.abs(np.diff(a, axis=0)).sum() + np.abs(np.diff(a, axis=1)).sum())
+    assert tv(u) < tv(y)
+    # divergence-form members keep the mean of every frame (the Getreuer variants repeat the first row / column in
+    # the backward difference, tvdenoise_cham_*.m:54-57, and do not)
+    if "cham" not in name:
+        np.testing.assert_allclose(u.mean(axis=(0, 1)), y.mean(axis=(0, 1)), atol=2e-6)
+    # per-frame members treat the frames independently; the ITV3D members couple them
+    one = fn(y[:, :, 1:2].copy(), _lam(name), 4)[:, :, 0]
+    if "ITV3D" in name:
+        assert np.abs(one - u[:, :, 1]).max() > 1e-4
+    else:
+        np.testing.assert_array_equal(one, u[:, :, 1])
+
+
+def test_matlab_cham_itv2d_equals_the_2d_transliteration():
+    """The 3-D branch of tvdenoise_cham_ITV2D.m (:73-90) applied to one frame is its 2-D branch (:59-72),
+    transliterated independently above (_matlab_itv2d)."""
+    from oracle import matlab_tv as M
+    y = _frames((15, 19, 1), dtype=np.float64)
+    want = _matlab_itv2d(y[:, :, 0], 9.0, 6, 1.0 / 8)
+    np.testing.assert_allclose(M.tvdenoise_cham_ITV2D(y, 9.0, 6)[:, :, 0], want, rtol=0, atol=1e-14)
+
+
+def test_matlab_fgp_first_iterate_is_the_input_and_weights_follow_the_t_sequence():
+    """fgp_denoise_*.m:85: with R = 0 the first D is Xobs itself; MAXITER = 1 therefore returns the input."""
+    from oracle import matlab_tv as M
+    y = _frames((10, 12, 3))
+    for name in ("fgp_denoise_ATV2D", "fgp_denoise_ITV2D", "fgp_denoise_ITV3D"):
+        np.testing.assert_array_equal(getattr(M, name)(y, 0.1, 1), y)
