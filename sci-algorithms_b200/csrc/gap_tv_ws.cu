@@ -102,7 +102,9 @@ int fused_variant() {
 
 bool fused_ws_supported(const FusedArgs& a) {
     if (fused_variant() == 1) return false;
-    if (a.mode != MODE_GAP_ACC && a.mode != MODE_GAP_PLAIN && a.mode != MODE_TV) return false;
+    if (a.mode != MODE_GAP_ACC && a.mode != MODE_GAP_PLAIN && a.mode != MODE_TV && a.mode != MODE_ADMM) return false;
+    if (a.mode == MODE_ADMM && (!a.b_in || !a.b_out || a.b_in == a.b_out || !aligned16(a.b_in) || !aligned16(a.b_out) ||
+                                (a.xproj_out && !aligned16(a.xproj_out)))) return false;
     if (a.mask2d) return false;                                   // CASSI index-offset masks: stream kernel
     if (a.clip01) return false;
     const int Q = a.C / 2;
@@ -144,6 +146,7 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
     const int R = a.tv_iter_max - 1, Q = a.C / 2;
     WsParams p{};
     p.y1_out = a.y1_out;
+    p.b_in = a.b_in; p.b_out = a.b_out; p.xproj_out = a.xproj_out; p.gamma = a.gamma;
     p.energy = reinterpret_cast<double*>(a.workspace);
     p.ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.workspace) + fused_workspace_bytes(a.B, a.H, a.W, a.C, a.tv_iter_max) - 16);
     p.flag = (a.flag && R > 1) ? a.flag : nullptr;
@@ -244,7 +247,7 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
                 fprintf(stderr, "[ws prof] cta %lld own=%d grid=%lld\n", cta, own, ctas);
                 for (int w = 0; w < nwarp; ++w) {
                     const long long* r = &h[((size_t)cta * nwarp + w) * 4];
-                    if (w < ncw) fprintf(stderr, "  consumer %2d: total %9lld  wait f_full %9lld  wait out_empty %9lld\n", w, r[0], r[1], r[2]);
+                    if (WS_PROD_FIRST ? w >= NPROD : w < ncw) fprintf(stderr, "  consumer %2d: total %9lld  wait f_full %9lld  wait out_empty %9lld\n", w, r[0], r[1], r[2]);
                     else fprintf(stderr, "  producer %2d: total %9lld  wait raw %9lld  wait f_empty(+stores) %9lld  bar %9lld\n", w, r[0], r[1], r[2], r[3]);
                 }
             }

@@ -46,6 +46,9 @@ using namespace fusedk;     // PTX helpers, P2 arithmetic
 #ifndef WS_PATH3
 #define WS_PATH3 1        // 1: first / last blocks of a row segment whose rows all exist take an unrolled path with energy masks only
 #endif
+#ifndef WS_PROD_FIRST
+#define WS_PROD_FIRST 0   // 1: the producer-side warps take warp ids 0..3 and the consumers 4..: the arbiter prefers high warp
+#endif                    // ids, so the consumers (the bottleneck) win ties and the producers fill the gaps
 #ifndef WS_SANITIZE
 #define WS_SANITIZE 0     // 1: every lane arrives on the mbarriers (counts x 32) instead of one elected lane behind a __syncwarp:
 #endif                    // same protocol, but visible thread by thread to compute-sanitizer's racecheck (tools/sanitize.sh)
@@ -64,6 +67,11 @@ constexpr int NOUT = 2;           // ring depth of the output tiles
 
 struct WsParams {
     float* y1_out;                // accelerated GAP: y1 written by the producers
+    // ADMM (MODE_ADMM): x_in = theta; the multiplier b is read by the projection threads straight from global memory
+    // (L1/L2, no staging: the raw ring has no room for a third frame tile) and b_new = theta_new - f is written by the
+    // consumers; x = f + b only where the caller wants it (xproj_out, may be null)
+    const float* b_in; float* b_out; float* xproj_out;
+    float gamma;
     double* energy;               // [B][C][R] partial sums of d^2 + w*|g|
     int* flag;                    // early-stop flag (may be null: no check)
     unsigned* ticket;             // last-CTA detection for the in-kernel energy check
@@ -386,7 +394,7 @@ struct WsSegIter {
     }
 };
 
-// MODE: MODE_GAP_ACC, MODE_GAP_PLAIN or MODE_TV (the denoiser alone: f = x_in).  Q = C/2 channel pairs.
+// MODE: MODE_GAP_ACC, MODE_GAP_PLAIN, MODE_ADMM or MODE_TV (the denoiser alone: f = x_in).  Q = C/2 channel pairs.
 template <int R, int MODE, int Q>
 __global__ void __launch_bounds__(ws_threads(Q), 1)
 gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
@@ -430,10 +438,13 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
     // Register reallocation between the roles (warpgroups of four warps): the producers give registers back, the
     // consumers -- whose pipeline state fills the 128 registers a 512-thread CTA starts with -- take them.
     constexpr bool kRealloc = WS_CREGS > 0 && CW % 4 == 0 && ws_threads(Q) == 512;
-    if (warp < CW) {
+    // role of this warp: consumer index cwarp (0..CW-1) or producer-side index pwarp (0 = TMA warp, 1..NCOMP projection)
+    const int cwarp = WS_PROD_FIRST ? warp - NPROD : (warp < CW ? warp : -1);
+    const int pwarp = WS_PROD_FIRST ? warp : warp - CW;
+    if (cwarp >= 0) {
         // =================================== consumers ===================================
         if (kRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_CREGS > 0 ? WS_CREGS : 128));
-        const int gi = warp / Q, q = warp - gi * Q;
+        const int gi = cwarp / Q, q = cwarp - gi * Q;
         // f tile: [WRB][NGRP][Q][GW][2] floats; this lane reads 16 bytes (A.c0 A.c1 B.c0 B.c1)
         const uint32_t f_lane = smem_base + L.f_off + ((gi * Q + q) * GW + 2 * lane) * 8;
         constexpr int F_ROW = NGRP * Q * GW * 8;
@@ -488,6 +499,15 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             auto f_old_addr = [&](int j) { return j >= R ? fsrc + (j - R) * F_ROW : fprev + (j - R + WRB) * F_ROW; };
             const int t0 = rs + blk * WRB;
             const bool rows_fast = t0 >= fast_lo && t0 + WRB - 1 <= fast_hi;
+            // ADMM multiplier: x = f + b, so b - (x - theta_new) = theta_new - f, and f(t-R) is the row that closes the
+            // last stage.  Written straight to global memory (two 8-byte stores per lane; the channel pairs of the other
+            // consumer warps complete the sectors in L2).
+            auto store_b = [&](int orow, const P2 (&o)[2], const P2 (&fo)[2], bool check_rows) {
+                if (!own_lane || (check_rows && (orow < r0 || orow >= r1))) return;
+                float* dst = p.b_out + (((size_t)b * H + orow) * W + pxa) * C + 2 * q;
+                *reinterpret_cast<float2*>(dst) = make_float2(o[0].x - fo[0].x, o[0].y - fo[0].y);
+                *reinterpret_cast<float2*>(dst + C) = make_float2(o[1].x - fo[1].x, o[1].y - fo[1].y);
+            };
             auto fast_block = [&](auto path) {
                 constexpr int PATH = decltype(path)::value;
 #pragma unroll
@@ -504,6 +524,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                         asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW), "f"(o[0].x), "f"(o[0].y) : "memory");
                         asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW + 16), "f"(o[1].x), "f"(o[1].y) : "memory");
                     }
+                    if (MODE == MODE_ADMM) store_b(t0 + j - R, o, f_old, PATH == 3);
                 }
             };
             // every row touched exists (warm-up done, f(t-R) in the ring) and lies inside the image; steps past t_end
@@ -537,6 +558,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                             asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW), "f"(o[0].x), "f"(o[0].y) : "memory");
                             asm volatile("st.shared.v2.f32 [%0], {%1,%2};\n" ::"r"(odst + j * O_ROW + 16), "f"(o[1].x), "f"(o[1].y) : "memory");
                         }
+                        if (MODE == MODE_ADMM) store_b(t - R, o, f_old, true);
                     }
                 }
             }
@@ -573,9 +595,10 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
         constexpr int NPT = NCOMP * 32;
         constexpr int NITEM = WRB * NGRP * GW;                   // (row, group, pixel) items per block
         constexpr bool TVONLY = MODE == MODE_TV;                 // standalone denoiser: f is the input itself
+        constexpr bool ADMM = MODE == MODE_ADMM;
         constexpr uint32_t kTx = TVONLY ? (uint32_t)L.x_bytes
                                         : 2u * L.x_bytes + (MODE == MODE_GAP_ACC ? 3u : 2u) * NGRP * WRB * GW * 4;
-        if (warp == CW) {
+        if (pwarp == 0) {
             // ------------- the TMA warp: lane 0 loads, lane 1 stores, each walking the block sequence on its own.
             // Neither ever waits for the other, and the projection warps never wait for a store: a finished output
             // block leaves for HBM as soon as the last consumer warp has arrived.
@@ -646,7 +669,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             }
         } else {
         // ------------- projection warps
-        const int ptid = tid - (CW + 1) * 32;                    // 0 .. NCOMP*32-1
+        const int ptid = (pwarp - 1) * 32 + lane;                // 0 .. NCOMP*32-1
         long long pw0 = 0, pw1 = 0, pw2 = 0;
         const long long pstart = p.prof ? clock64() : 0;
         const float lam = p.lambda;
@@ -672,6 +695,22 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             if (p.prof) pw1 += clock64() - c1;
             const unsigned char* raw = smem_raw + slot * L.raw_bytes;
             unsigned char* fdst = smem_raw + L.f_off + fs * L.f_bytes;
+            if constexpr (ADMM) {
+                // the multiplier is read straight from global memory: start all of this thread's lines now, so that
+                // the item loop below (one item at a time) finds them in L1 instead of paying a DRAM round trip each
+#pragma unroll 1
+                for (int itx = ptid; itx < NITEM; itx += NPT) {
+                    const int px = itx & (GW - 1), g = (itx / GW) % NGRP, j = itx / (GW * NGRP);
+                    const int row = rs + blk * WRB + j;
+                    const int gpx = (group0 + g) * own - HALO + px;
+                    if ((group0 + g) < p.ngroups && gpx >= 0 && gpx < W && row < H) {
+                        const float* bp = p.b_in + (((size_t)it.b * H + row) * W + gpx) * C;
+#pragma unroll
+                        for (int c8 = 0; c8 < C; c8 += 8)
+                            asm volatile("prefetch.global.L1 [%0];\n" ::"l"(bp + c8));
+                    }
+                }
+            }
 #pragma unroll 1
             for (int itx = ptid; itx < NITEM; itx += NPT) {
                 const int px = itx & (GW - 1), g = (itx / GW) % NGRP, j = itx / (GW * NGRP);
@@ -696,10 +735,18 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
 #pragma unroll
                 for (int k0 = 0; k0 < K; ++k0) { xv[k0] = tx[k0 ^ lsw]; pv[k0] = tp[k0 ^ lsw]; }
                 P2 acc2 = splat(0.f);
+                // ADMM: this pixel's multiplier, C contiguous floats in global memory (zero outside the image)
+                const size_t goff = ADMM ? (((size_t)it.b * H + (row < H ? row : 0)) * W + (in ? gpx : 0)) * C : 0;
+                const float4* bsrc = ADMM ? reinterpret_cast<const float4*>(p.b_in + goff) : nullptr;
 #pragma unroll
                 for (int k0 = 0; k0 < K; ++k0) {
-                    acc2 = fma2(make_float2(xv[k0].x, xv[k0].y), make_float2(pv[k0].x, pv[k0].y), acc2);
-                    acc2 = fma2(make_float2(xv[k0].z, xv[k0].w), make_float2(pv[k0].z, pv[k0].w), acc2);
+                    float4 u = xv[k0];
+                    if (ADMM && in) {                                // u = theta + b enters the dot product
+                        const float4 bq = __ldg(bsrc + (k0 ^ lsw));
+                        u.x += bq.x; u.y += bq.y; u.z += bq.z; u.w += bq.w;
+                    }
+                    acc2 = fma2(make_float2(u.x, u.y), make_float2(pv[k0].x, pv[k0].y), acc2);
+                    acc2 = fma2(make_float2(u.z, u.w), make_float2(pv[k0].z, pv[k0].w), acc2);
                 }
                 const float acc = acc2.x + acc2.y;
                 const float* sm = reinterpret_cast<const float*>(raw + L.small_off) + (g * WRB + j) * GW + px;
@@ -715,15 +762,24 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                         if (p.y1_dn != nullptr && row >= p.out_hi - R) p.y1_dn[idx] = y1n;
                     }
                     sv = (y1n - acc) * fast_rcp(psv);
+                } else if (ADMM) {
+                    sv = (yv - acc) * fast_rcp(psv + p.gamma);
                 } else {
                     sv = (yv - acc) * fast_rcp(psv);
                 }
                 const P2 s2 = splat(in ? sv * lam : 0.f);
+                const bool want_x = ADMM && p.xproj_out != nullptr && in && px >= HALO && px < HALO + own && row >= r0 && row < r1;
 #pragma unroll
                 for (int k0 = 0; k0 < K; ++k0) {
                     const int kc = k0 ^ lsw;
-                    frow[(2 * kc) * GW] = fma2(s2, make_float2(pv[k0].x, pv[k0].y), make_float2(xv[k0].x, xv[k0].y));
-                    frow[(2 * kc + 1) * GW] = fma2(s2, make_float2(pv[k0].z, pv[k0].w), make_float2(xv[k0].z, xv[k0].w));
+                    const P2 f01 = fma2(s2, make_float2(pv[k0].x, pv[k0].y), make_float2(xv[k0].x, xv[k0].y));
+                    const P2 f23 = fma2(s2, make_float2(pv[k0].z, pv[k0].w), make_float2(xv[k0].z, xv[k0].w));
+                    frow[(2 * kc) * GW] = f01;                       // TV input: f = theta + lambda*s*Phi = x - b
+                    frow[(2 * kc + 1) * GW] = f23;
+                    if (ADMM && want_x) {                            // x = f + b (the projection output the caller reads)
+                        const float4 bq = __ldg(bsrc + kc);
+                        reinterpret_cast<float4*>(p.xproj_out + goff)[kc] = make_float4(f01.x + bq.x, f01.y + bq.y, f23.x + bq.z, f23.y + bq.w);
+                    }
                 }
             }
             __syncwarp();
@@ -836,6 +892,7 @@ int ws_launch_mode(int Q, const WsParams& p, const WsMaps& maps, int grid, cudaS
     template <> int ws_launch_r<RR>(int mode, int Q, const WsParams& p, const WsMaps& maps, int grid, cudaStream_t st) { \
         if (mode == MODE_GAP_ACC) return ws_launch_mode<RR, MODE_GAP_ACC>(Q, p, maps, grid, st);                 \
         if (mode == MODE_TV) return ws_launch_mode<RR, MODE_TV>(Q, p, maps, grid, st);                           \
+        if (mode == MODE_ADMM) return ws_launch_mode<RR, MODE_ADMM>(Q, p, maps, grid, st);                       \
         return ws_launch_mode<RR, MODE_GAP_PLAIN>(Q, p, maps, grid, st);                                         \
     }
 

@@ -293,7 +293,7 @@ static int step_exact(scipnp_solver* s, int k, cudaStream_t st) {
     return SCIPNP_OK;
 }
 
-static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
+static int step_fused(scipnp_solver* s, int k, bool last, cudaStream_t st) {
     const scipnp_params& p = s->p;
     FusedArgs a{};
     a.x_in = s->xa; a.x_out = s->xb;
@@ -312,6 +312,12 @@ static int step_fused(scipnp_solver* s, int k, cudaStream_t st) {
     } else {
         a.mode = MODE_ADMM;
         a.b_in = s->ba; a.b_out = s->bb; a.xproj_out = s->xproj;
+        // x (the projection output) is only read by the PSNR track and by the caller after the last step; the
+        // warp-specialised kernel can leave it out (the stream kernel always writes it)
+        if (!(s->has_orig || last)) {
+            a.xproj_out = nullptr;
+            if (!fused_ws_supported(a)) a.xproj_out = s->xproj;
+        }
     }
     TilePush tp{};
     const bool push = s->tiled && s->push_enabled && (s->up.present || s->dn.present);
@@ -387,7 +393,7 @@ int scipnp_solver_step_async(scipnp_solver* s, int iters, void* stream) {
     if (!s->use_fused)
         if (int e = ensure_exact_buffers(s)) return e;
     for (int i = 0; i < iters; ++i)
-        if (int e = s->use_fused ? step_fused(s, s->iters_done + i, st) : step_exact(s, s->iters_done + i, st)) return e;
+        if (int e = s->use_fused ? step_fused(s, s->iters_done + i, i + 1 == iters, st) : step_exact(s, s->iters_done + i, st)) return e;
     s->iters_done += iters;
     if (s->has_orig) s->psnr_count = s->iters_done < kPsnrCap / p.B ? s->iters_done : kPsnrCap / p.B;
     return SCIPNP_OK;

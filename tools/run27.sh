@@ -1,0 +1,9 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+E=$PWD/sci-algorithms_b200/build/exp
+for i in 1 2; do
+echo "main  : $(timeout 200 python profiles/prof_driver.py 40 2>&1 | tail -1)"
+echo "pfirst: $(SCIPNP_LIB=$E/libscipnp_pfirst.so timeout 200 python profiles/prof_driver.py 40 2>&1 | tail -1)"
+done
+echo "main 278  : $(timeout 200 python profiles/prof_driver.py 40 278 3840 24 2>&1 | tail -1)"
+echo "pfirst 278: $(SCIPNP_LIB=$E/libscipnp_pfirst.so timeout 200 python profiles/prof_driver.py 40 278 3840 24 2>&1 | tail -1)"
+SCIPNP_LIB=$E/libscipnp_pfirst.so SCIPNP_WS_PROF=1 timeout 300 python profiles/prof_driver.py 6 2>&1 | grep "ws prof\|consumer\|producer" | head -19
