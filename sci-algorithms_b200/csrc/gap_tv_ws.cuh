@@ -695,22 +695,6 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             if (p.prof) pw1 += clock64() - c1;
             const unsigned char* raw = smem_raw + slot * L.raw_bytes;
             unsigned char* fdst = smem_raw + L.f_off + fs * L.f_bytes;
-            if constexpr (ADMM) {
-                // the multiplier is read straight from global memory: start all of this thread's lines now, so that
-                // the item loop below (one item at a time) finds them in L1 instead of paying a DRAM round trip each
-#pragma unroll 1
-                for (int itx = ptid; itx < NITEM; itx += NPT) {
-                    const int px = itx & (GW - 1), g = (itx / GW) % NGRP, j = itx / (GW * NGRP);
-                    const int row = rs + blk * WRB + j;
-                    const int gpx = (group0 + g) * own - HALO + px;
-                    if ((group0 + g) < p.ngroups && gpx >= 0 && gpx < W && row < H) {
-                        const float* bp = p.b_in + (((size_t)it.b * H + row) * W + gpx) * C;
-#pragma unroll
-                        for (int c8 = 0; c8 < C; c8 += 8)
-                            asm volatile("prefetch.global.L1 [%0];\n" ::"l"(bp + c8));
-                    }
-                }
-            }
 #pragma unroll 1
             for (int itx = ptid; itx < NITEM; itx += NPT) {
                 const int px = itx & (GW - 1), g = (itx / GW) % NGRP, j = itx / (GW * NGRP);
