@@ -105,6 +105,10 @@ bool fused_ws_supported(const FusedArgs& a) {
     if (a.mode != MODE_GAP_ACC && a.mode != MODE_GAP_PLAIN && a.mode != MODE_TV && a.mode != MODE_ADMM) return false;
     if (a.mode == MODE_ADMM && (!a.b_in || !a.b_out || a.b_in == a.b_out || !aligned16(a.b_in) || !aligned16(a.b_out) ||
                                 (a.xproj_out && !aligned16(a.xproj_out)))) return false;
+    // ADMM with few channels stays on the stream kernel: the projection threads read the multiplier from global memory
+    // pixel by pixel, and at C = 8 that makes them the slower side (28x256x256x8: 0.20 ms against 0.15); at C = 24
+    // (3840x2160) the warp-specialised kernel wins, 1.20 ms against 1.64
+    if (a.mode == MODE_ADMM && a.C < 12) return false;
     if (a.mask2d) return false;                                   // CASSI index-offset masks: stream kernel
     if (a.clip01) return false;
     const int Q = a.C / 2;

@@ -104,8 +104,11 @@ struct WsParams {
 
 struct WsMaps { CUtensorMap x, phi, y, y1, ps, out, out_up, out_dn; };
 
-// pixel groups per CTA for Q = C/2 channel pairs: about 12 consumer warps
-__host__ __device__ constexpr int ws_groups(int Q) { return 12 / Q < 1 ? 1 : 12 / Q; }
+// pixel groups per CTA for Q = C/2 channel pairs: about 12 consumer warps -- but 8 for C = 4 and C = 8: with 12 their
+// staging planes (three per group) leave room for two f slots only, and since an f slot is handed back one block late
+// the projection warps and the consumers then take turns instead of overlapping (measured at 28x256x256x8: both
+// sides waiting half of the time)
+__host__ __device__ constexpr int ws_groups(int Q) { return Q <= 4 ? 8 / Q : (12 / Q < 1 ? 1 : 12 / Q); }
 __host__ __device__ constexpr int ws_consumers(int Q) { return ws_groups(Q) * Q; }
 __host__ __device__ constexpr int ws_threads(int Q) { return (ws_consumers(Q) + NPROD) * 32; }
 
@@ -129,7 +132,7 @@ __host__ __device__ constexpr WsSmem ws_smem(int Q) {
     s.out_sub = (Q / 2) * OWN_MAX * 16;
     s.out_bytes = WRB * NGRP * s.out_sub;
     const int fixed = s.f_off + NOUT * s.out_bytes + 256;
-    s.nf = (fixed + 3 * s.f_bytes <= 232448 - 1024) ? 3 : 2;
+    s.nf = (fixed + 4 * s.f_bytes <= 232448 - 1024) ? 4 : (fixed + 3 * s.f_bytes <= 232448 - 1024) ? 3 : 2;
     s.out_off = s.f_off + s.nf * s.f_bytes;
     s.bar_off = s.out_off + NOUT * s.out_bytes;
     s.total = s.bar_off + 256;
