@@ -112,9 +112,10 @@ __global__ void At_kernel_v4(const float* __restrict__ y, const float4* __restri
 
 // Start of a reconstruction in one pass over the mask stack: Phi_sum (mask_sum, pnp_sci_algo.py:491-492, NumPy's
 // summation order) and the default initial guess x0 = At(y) (pnp_sci_algo.py:621-622).  A CTA owns kInitP consecutive
-// pixels: coalesced 128-bit loads of Phi, x0 written straight from the loaded registers, the masks parked in shared
-// memory (row stride C+1: conflict-free) for the one-thread-per-pixel sum.
-constexpr int kInitP = 64, kInitThreads = 256;
+// pixels: every thread first issues all of its coalesced 128-bit loads of Phi (up to kInitL in flight), writes x0
+// from the registers and parks the masks in shared memory (row stride C+1: conflict-free for the reader), then one
+// thread per pixel sums its C values.
+constexpr int kInitP = 256, kInitThreads = 256, kInitL = 8;
 __global__ void __launch_bounds__(kInitThreads)
 init_x0_phisum_kernel(const float* __restrict__ y, const float4* __restrict__ Phi, float4* __restrict__ x,
                       float* __restrict__ phisum, long long npix, int C4, long long phi_stride4, int phisum_batched) {
@@ -125,13 +126,25 @@ init_x0_phisum_kernel(const float* __restrict__ y, const float4* __restrict__ Ph
     const float4* src = Phi + (size_t)b * phi_stride4 + (size_t)p0 * C4;
     float4* dst = x + ((size_t)b * npix + p0) * C4;
     const float* yb = y + (size_t)b * npix + p0;
-    for (int i = threadIdx.x; i < n * C4; i += kInitThreads) {
-        const float4 m = src[i];
-        const int px = i / C4, k = i - px * C4;
-        const float yv = yb[px];
-        dst[i] = make_float4(__fmul_rn(yv, m.x), __fmul_rn(yv, m.y), __fmul_rn(yv, m.z), __fmul_rn(yv, m.w));
-        float* r = sm_init + px * ld + 4 * k;
-        r[0] = m.x; r[1] = m.y; r[2] = m.z; r[3] = m.w;
+    const int total = n * C4;
+    for (int base = 0; base < total; base += kInitThreads * kInitL) {
+        float4 m[kInitL];
+#pragma unroll
+        for (int l = 0; l < kInitL; ++l) {
+            const int i = base + l * kInitThreads + threadIdx.x;
+            if (i < total) m[l] = src[i];
+        }
+#pragma unroll
+        for (int l = 0; l < kInitL; ++l) {
+            const int i = base + l * kInitThreads + threadIdx.x;
+            if (i < total) {
+                const int px = i / C4, k = i - px * C4;
+                const float yv = yb[px];
+                dst[i] = make_float4(__fmul_rn(yv, m[l].x), __fmul_rn(yv, m[l].y), __fmul_rn(yv, m[l].z), __fmul_rn(yv, m[l].w));
+                float* r = sm_init + px * ld + 4 * k;
+                r[0] = m[l].x; r[1] = m[l].y; r[2] = m[l].z; r[3] = m[l].w;
+            }
+        }
     }
     if (!phisum_batched && b != 0) return;            // one Phi_sum for all measurements: the first slice writes it
     __syncthreads();
@@ -391,10 +404,10 @@ using namespace scipnp;
 namespace scipnp {
 int launch_init_x0_phisum(const float* y, const float* Phi, float* x, float* phisum, int B, int H, int W, int C,
                           int phi_batched, cudaStream_t st) {
-    if ((C & 3) != 0 || C > kMaxLocalC || !aligned16(Phi) || !aligned16(x)) return SCIPNP_EINVAL;
+    const size_t smem = (size_t)kInitP * (C + 1) * sizeof(float);
+    if ((C & 3) != 0 || C > kMaxLocalC || smem > 48 * 1024 || !aligned16(Phi) || !aligned16(x)) return SCIPNP_EINVAL;
     const long long npix = (long long)H * W;
     dim3 grid((unsigned)ceil_div_ll(npix, kInitP), B);
-    const size_t smem = (size_t)kInitP * (C + 1) * sizeof(float);
     init_x0_phisum_kernel<<<grid, kInitThreads, smem, st>>>(y, reinterpret_cast<const float4*>(Phi), reinterpret_cast<float4*>(x),
                                                            phisum, npix, C / 4, phi_batched ? npix * (C / 4) : 0, phi_batched ? 1 : 0);
     count_launch();

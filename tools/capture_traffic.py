@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""profiles/traffic.json from an `ncu --set full` report of the fused kernel, stamped with the hash of the kernel
-sources it was measured on.  bench.py reports roofline.traffic only while that hash equals the hash of the
+"""profiles/traffic.json from an `ncu --set full` report of the fused kernel, stamped with the hash of the kernel's
+device sources (gap_tv_ws.cuh, gap_tv_stream.cuh, ws_inst_r4.cu) as they were when it was measured.  bench.py reports roofline.traffic only while that hash equals the hash of the
 sources in the tree (a stale capture reads as null).
 
     python tools/capture_traffic.py gpurun_out/<report>.ncu-rep [kernel-index]
@@ -16,12 +16,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+KERNEL_SOURCES = ("gap_tv_ws.cuh", "gap_tv_stream.cuh", "ws_inst_r4.cu")     # the device code of the measured kernel
+
+
 def source_hash():
     h = hashlib.sha256()
-    for p in sorted(glob.glob(os.path.join(ROOT, "sci-algorithms_b200", "csrc", "*"))):
-        if p.endswith((".cu", ".cuh")):
-            h.update(os.path.basename(p).encode())
-            h.update(open(p, "rb").read())
+    for name in KERNEL_SOURCES:
+        p = os.path.join(ROOT, "sci-algorithms_b200", "csrc", name)
+        h.update(name.encode())
+        h.update(open(p, "rb").read())
     return h.hexdigest()[:16]
 
 
