@@ -20,12 +20,13 @@ int g_variant = -1;      // -1: from the environment (SCIPNP_FUSED_VARIANT), 0: 
 struct MapKey {
     const float *x_in, *x_out, *phi, *y, *y1, *ps;
     int B, H, W, C, own, phi_batched;
+    const float* b_in = nullptr;                       // ADMM with a staged multiplier
     const float *x_up = nullptr, *x_dn = nullptr;      // halo push: the neighbours' output buffers and their row counts
     int up_rows = 0, dn_rows = 0;
     bool operator==(const MapKey& o) const {
         return x_in == o.x_in && x_out == o.x_out && phi == o.phi && y == o.y && y1 == o.y1 && ps == o.ps &&
                B == o.B && H == o.H && W == o.W && C == o.C && own == o.own && phi_batched == o.phi_batched &&
-               x_up == o.x_up && x_dn == o.x_dn && up_rows == o.up_rows && dn_rows == o.dn_rows;
+               x_up == o.x_up && x_dn == o.x_dn && up_rows == o.up_rows && dn_rows == o.dn_rows && b_in == o.b_in;
     }
 };
 struct MapEntry { MapKey key; WsMaps maps; bool valid = false; unsigned long long stamp = 0; };
@@ -41,6 +42,8 @@ int build_maps(const MapKey& k, WsMaps* m) {
         unsigned long long str[2] = {(unsigned long long)k.C * 4, (unsigned long long)k.W * k.C * 4};
         unsigned box[3] = {(unsigned)k.C, GW, WRB};
         if (int e = make_tensor_map_f32(&m->x, k.x_in, 3, dims, str, box, 1)) return e;
+        m->b = m->x;
+        if (k.b_in) if (int e = make_tensor_map_f32(&m->b, k.b_in, 3, dims, str, box, 1)) return e;
         dims[2] = prows;
         if (int e = make_tensor_map_f32(&m->phi, k.phi, 3, dims, str, box, 1)) return e;
     }
@@ -108,7 +111,7 @@ bool fused_ws_supported(const FusedArgs& a) {
     // ADMM with few channels stays on the stream kernel: the projection threads read the multiplier from global memory
     // pixel by pixel, and at C = 8 that makes them the slower side (28x256x256x8: 0.20 ms against 0.15); at C = 24
     // (3840x2160) the warp-specialised kernel wins, 1.20 ms against 1.64
-    if (a.mode == MODE_ADMM && a.C < 12) return false;
+    if (a.mode == MODE_ADMM && a.C < 12 && !ws_bstage(a.C / 2)) return false;
     if (a.mask2d) return false;                                   // CASSI index-offset masks: stream kernel
     if (a.clip01) return false;
     const int Q = a.C / 2;
@@ -187,6 +190,7 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
     if (a.mode == MODE_TV) {          // the denoiser alone stages its input only; the other descriptors are never used
         key.phi = a.x_in; key.y = a.x_in; key.ps = a.x_in; key.phi_batched = 1;
     }
+    if (a.mode == MODE_ADMM && ws_bstage(Q)) key.b_in = a.b_in;
     if (a.push) {
         const TilePush& t = *a.push;
         if (a.B != 1 || (!t.x_up && !t.x_dn)) { set_error("halo push: one scene, at least one neighbour"); return SCIPNP_EINVAL; }
@@ -265,7 +269,7 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
 void fused_ws_forget(const void* base) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (auto& e : g_cache)
-        if (e.valid && (e.key.x_in == base || e.key.x_out == base || e.key.phi == base || e.key.x_up == base || e.key.x_dn == base)) e.valid = false;
+        if (e.valid && (e.key.x_in == base || e.key.x_out == base || e.key.phi == base || e.key.x_up == base || e.key.x_dn == base || e.key.b_in == base)) e.valid = false;
 }
 
 }  // namespace scipnp

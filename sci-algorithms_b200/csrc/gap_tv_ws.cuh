@@ -102,7 +102,7 @@ struct WsParams {
     int* timeout_flag;
 };
 
-struct WsMaps { CUtensorMap x, phi, y, y1, ps, out, out_up, out_dn; };
+struct WsMaps { CUtensorMap x, phi, y, y1, ps, out, out_up, out_dn, b; };
 
 // pixel groups per CTA for Q = C/2 channel pairs: about 12 consumer warps -- but 8 for C = 4 and C = 8: with 12 their
 // staging planes (three per group) leave room for two f slots only, and since an f slot is handed back one block late
@@ -121,11 +121,12 @@ struct WsSmem {
     int bar_off;
     int total;
 };
-__host__ __device__ constexpr WsSmem ws_smem(int Q) {
+// `bstage`: a third frame tile per raw slot (ADMM: the multiplier b staged by TMA next to theta and Phi)
+__host__ __device__ constexpr WsSmem ws_smem(int Q, bool bstage = false) {
     WsSmem s{};
     const int NGRP = ws_groups(Q), C = 2 * Q;
     s.x_bytes = NGRP * WRB * GW * C * 4;
-    s.small_off = 2 * s.x_bytes;
+    s.small_off = (bstage ? 3 : 2) * s.x_bytes;
     s.raw_bytes = s.small_off + 3 * NGRP * WRB * GW * 4;
     s.f_off = NRAW * s.raw_bytes;
     s.f_bytes = WRB * NGRP * Q * GW * 2 * 4;
@@ -137,6 +138,11 @@ __host__ __device__ constexpr WsSmem ws_smem(int Q) {
     s.bar_off = s.out_off + NOUT * s.out_bytes;
     s.total = s.bar_off + 256;
     return s;
+}
+// ADMM: is there room to stage the multiplier as well and still keep three f slots?  (C = 4, 8, 16, 20: yes;
+// C = 12, 24: no -- there the projection threads read it from global memory)
+__host__ __device__ constexpr bool ws_bstage(int Q) {
+    return ws_smem(Q, true).nf >= 3 && ws_smem(Q, true).total <= 232448 - 1024;
 }
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -404,7 +410,8 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
     constexpr int NGRP = ws_groups(Q);
     constexpr int CW = ws_consumers(Q);
     constexpr int C = 2 * Q, K = Q / 2;
-    constexpr WsSmem L = ws_smem(Q);
+    constexpr bool BST = MODE == MODE_ADMM && ws_bstage(Q);       // the multiplier is staged by TMA like theta and Phi
+    constexpr WsSmem L = ws_smem(Q, BST);
     constexpr int NF = L.nf;
     static_assert(Q % 2 == 0, "C must be a multiple of 4");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -600,7 +607,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
         constexpr bool TVONLY = MODE == MODE_TV;                 // standalone denoiser: f is the input itself
         constexpr bool ADMM = MODE == MODE_ADMM;
         constexpr uint32_t kTx = TVONLY ? (uint32_t)L.x_bytes
-                                        : 2u * L.x_bytes + (MODE == MODE_GAP_ACC ? 3u : 2u) * NGRP * WRB * GW * 4;
+                                        : (BST ? 3u : 2u) * L.x_bytes + (MODE == MODE_GAP_ACC ? 3u : 2u) * NGRP * WRB * GW * 4;
         if (pwarp == 0) {
             // ------------- the TMA warp: lane 0 loads, lane 1 stores, each walking the block sequence on its own.
             // Neither ever waits for the other, and the projection warps never wait for a store: a finished output
@@ -630,6 +637,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                             tma_load_3d(dst + g2 * (WRB * GW * C * 4), &maps.x, 0, px0, rowc, bar);
                             if (TVONLY) continue;
                             tma_load_3d(dst + L.x_bytes + g2 * (WRB * GW * C * 4), &maps.phi, 0, px0, prow, bar);
+                            if (BST) tma_load_3d(dst + 2 * L.x_bytes + g2 * (WRB * GW * C * 4), &maps.b, 0, px0, rowc, bar);
                             const uint32_t ds = dst + L.small_off + g2 * (WRB * GW * 4);
                             tma_load_2d(ds, &maps.y, px0, rowc, bar);
                             if (MODE == MODE_GAP_ACC) tma_load_2d(ds + NGRP * WRB * GW * 4, &maps.y1, px0, rowc, bar);
@@ -724,12 +732,13 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 P2 acc2 = splat(0.f);
                 // ADMM: this pixel's multiplier, C contiguous floats in global memory (zero outside the image)
                 const size_t goff = ADMM ? (((size_t)it.b * H + (row < H ? row : 0)) * W + (in ? gpx : 0)) * C : 0;
-                const float4* bsrc = ADMM ? reinterpret_cast<const float4*>(p.b_in + goff) : nullptr;
+                // staged: the tile next to Phi's (same layout as theta's, so the same chunk order k0 ^ lsw applies)
+                const float4* bsrc = !ADMM ? nullptr : BST ? tx + 2 * (L.x_bytes / 16) : reinterpret_cast<const float4*>(p.b_in + goff);
 #pragma unroll
                 for (int k0 = 0; k0 < K; ++k0) {
                     float4 u = xv[k0];
                     if (ADMM && in) {                                // u = theta + b enters the dot product
-                        const float4 bq = __ldg(bsrc + (k0 ^ lsw));
+                        const float4 bq = BST ? bsrc[k0 ^ lsw] : __ldg(bsrc + (k0 ^ lsw));
                         u.x += bq.x; u.y += bq.y; u.z += bq.z; u.w += bq.w;
                     }
                     acc2 = fma2(make_float2(u.x, u.y), make_float2(pv[k0].x, pv[k0].y), acc2);
@@ -764,7 +773,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     frow[(2 * kc) * GW] = f01;                       // TV input: f = theta + lambda*s*Phi = x - b
                     frow[(2 * kc + 1) * GW] = f23;
                     if (ADMM && want_x) {                            // x = f + b (the projection output the caller reads)
-                        const float4 bq = __ldg(bsrc + kc);
+                        const float4 bq = BST ? bsrc[kc] : __ldg(bsrc + kc);
                         reinterpret_cast<float4*>(p.xproj_out + goff)[kc] = make_float4(f01.x + bq.x, f01.y + bq.y, f23.x + bq.z, f23.y + bq.w);
                     }
                 }
@@ -838,7 +847,7 @@ template <int R> int ws_launch_r(int mode, int Q, const WsParams& p, const WsMap
 template <int R, int MODE, int Q>
 int ws_launch_q(const WsParams& p, const WsMaps& maps, int grid, cudaStream_t st) {
     auto kfn = gap_tv_ws_kernel<R, MODE, Q>;
-    constexpr WsSmem L = ws_smem(Q);
+    constexpr WsSmem L = ws_smem(Q, MODE == MODE_ADMM && ws_bstage(Q));
     static bool configured = false;
     if (!configured) {
         SCIPNP_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
