@@ -291,9 +291,9 @@ def measure_configs(torch, peak):
               iter_max=10, tv_weight=0.3, tv_iter_max=5)
     xo, _, _, _, pao = O.admmdenoise_cacti(meas, mask, A, At, **kw)
     xg, _, _, _, pag = scipnp.admmdenoise_cacti(meas, mask, A, At, **kw)
-    # ADMM: read theta, b, Phi (3NC) + y, Phi_sum (2N); write theta, b, x (3NC)
+    # ADMM: read theta, b, Phi (3NC) + y, Phi_sum (2N); write theta, b (2NC); x is written by the last step only
     entry("c2", "ADMM-TV 28 coded frames 256x256xCr=8 (one batch, per-frame masks)", ms,
-          F * 4 * 256 * 256 * (6 * 8 + 2), lpi, par(xg, xo, pag, pao, 10), path)
+          F * 4 * 256 * 256 * (5 * 8 + 2), lpi, par(xg, xo, pag, pao, 10), path)
 
     # c3: GAP-TV Bayer 512x512x24 = four 256x256x24 sub-lattices with their own masks
     y, Phi, orig = synth.make_bayer(512, 512, 24, cfg=3)
