@@ -184,6 +184,13 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
     p.own = own;
     p.ngroups = (a.W + own - 1) / own;
     p.nstrips = (p.ngroups + ws_groups(Q) - 1) / ws_groups(Q);
+    // several measurements whose groups do not fill the strips: lay all groups end to end (B = 28, W = 256, two groups
+    // per CTA: 70 strips instead of 84)
+    p.pack = (a.B > 1 && p.ngroups % ws_groups(Q) != 0 && !a.push && getenv("SCIPNP_WS_NO_PACK") == nullptr) ? 1 : 0;
+    if (p.pack) {
+        p.nstrips = (int)(((long long)a.B * p.ngroups + ws_groups(Q) - 1) / ws_groups(Q));
+        p.edge_cost = 0;
+    }
     const long long ctas = grid;
     MapKey key{a.x_in, a.x_out, a.Phi, a.y, a.mode == MODE_GAP_ACC ? a.y1_in : nullptr, a.Phi_sum,
                a.B, a.H, a.W, a.C, own, p.phi_batched};

@@ -62,7 +62,7 @@ constexpr int HALO = 4;           // halo pixels per side of a group (2 lanes)
 constexpr int OWN_MAX = GW - 2 * HALO;
 constexpr int NPROD = 4;          // producer-side warps: one TMA warp (loader lane + storer lane) and NCOMP projection warps
 constexpr int NCOMP = NPROD - 1;
-constexpr int NRAW = 2;           // ring depth of the raw (TMA-staged) tiles
+constexpr int kNrawMax = 3;       // ring depth of the raw (TMA-staged) tiles: ws_nraw(Q, bstage), 2 or 3
 constexpr int NOUT = 2;           // ring depth of the output tiles
 
 struct WsParams {
@@ -78,6 +78,8 @@ struct WsParams {
     double tv_eps;
     float lambda, tv_c, tv_w;     // tv_c = tau / weight
     int B, H, W, C;
+    int pack;                     // 1: the groups of all batch elements are laid end to end and a strip takes NGRP consecutive
+                                  // ones, whatever element they belong to (ngroups % NGRP != 0 would leave group slots empty)
     int own;                      // owned pixels per group (multiple of 4, <= OWN_MAX)
     int ngroups;                  // ceil(W / own)
     int nstrips;                  // ceil(ngroups / NGRP): column strips
@@ -104,6 +106,18 @@ struct WsParams {
 
 struct WsMaps { CUtensorMap x, phi, y, y1, ps, out, out_up, out_dn, b; };
 
+// Group slot gi of strip `strip` (of batch element b when the groups are not packed): batch element, group, live?
+struct WsSlot { int b, grp; bool live; };
+__device__ __forceinline__ WsSlot ws_slot(const WsParams& p, int b, int strip, int gi, int ngrp) {
+    if (!p.pack) {
+        const int grp = strip * ngrp + gi;
+        return WsSlot{b, grp, grp < p.ngroups};
+    }
+    const int G = strip * ngrp + gi, bb = G / p.ngroups;
+    if (bb >= p.B) return WsSlot{0, p.ngroups, false};            // past the last element: a dead slot (loads zero-fill)
+    return WsSlot{bb, G - bb * p.ngroups, true};
+}
+
 // pixel groups per CTA for Q = C/2 channel pairs: about 12 consumer warps -- but 8 for C = 4 and C = 8: with 12 their
 // staging planes (three per group) leave room for two f slots only, and since an f slot is handed back one block late
 // the projection warps and the consumers then take turns instead of overlapping (measured at 28x256x256x8: both
@@ -113,6 +127,7 @@ __host__ __device__ constexpr int ws_consumers(int Q) { return ws_groups(Q) * Q;
 __host__ __device__ constexpr int ws_threads(int Q) { return (ws_consumers(Q) + NPROD) * 32; }
 
 struct WsSmem {
+    int nraw;           // raw ring depth
     int x_bytes;        // x tiles of one raw slot: [NGRP][WRB][GW][C]
     int small_off;      // y / y1 / Phi_sum rows inside a raw slot: [3][NGRP][WRB][GW]
     int raw_bytes;      // one raw slot
@@ -128,12 +143,18 @@ __host__ __device__ constexpr WsSmem ws_smem(int Q, bool bstage = false) {
     s.x_bytes = NGRP * WRB * GW * C * 4;
     s.small_off = (bstage ? 3 : 2) * s.x_bytes;
     s.raw_bytes = s.small_off + 3 * NGRP * WRB * GW * 4;
-    s.f_off = NRAW * s.raw_bytes;
     s.f_bytes = WRB * NGRP * Q * GW * 2 * 4;
     s.out_sub = (Q / 2) * OWN_MAX * 16;
     s.out_bytes = WRB * NGRP * s.out_sub;
+    // Three raw slots where four f slots still fit beside them (C = 4, 8 without a staged multiplier: with eight
+    // consumer warps a block of four rows is consumed faster than a TMA round trip, and two slots starve the
+    // projection warps -- measured: they waited for data half of the time), else two.
+    const int lim = 232448 - 1024;
+    const int fix3 = 3 * s.raw_bytes + NOUT * s.out_bytes + 256;
+    s.nraw = (fix3 + 4 * s.f_bytes <= lim) ? 3 : 2;
+    s.f_off = s.nraw * s.raw_bytes;
     const int fixed = s.f_off + NOUT * s.out_bytes + 256;
-    s.nf = (fixed + 4 * s.f_bytes <= 232448 - 1024) ? 4 : (fixed + 3 * s.f_bytes <= 232448 - 1024) ? 3 : 2;
+    s.nf = (fixed + 4 * s.f_bytes <= lim) ? 4 : (fixed + 3 * s.f_bytes <= lim) ? 3 : 2;
     s.out_off = s.f_off + s.nf * s.f_bytes;
     s.bar_off = s.out_off + NOUT * s.out_bytes;
     s.total = s.bar_off + 256;
@@ -367,7 +388,7 @@ struct WsSegIter {
         Li = chg + Hw * wi; Le = chg + Hw * we;
         Tb = nstrips == 1 ? (long long)Le : 2LL * Le + (long long)(nstrips - 2) * Li;
         // total = q * grid + rem: the first `rem` CTAs take q + 1 ticks, the others q
-        const long long total = (long long)p.B * Tb;
+        const long long total = (long long)(p.pack ? 1 : p.B) * Tb;
         const long long q = total / gridDim.x, rem = total - q * gridDim.x, c = blockIdx.x;
         unit = c * q + (c < rem ? c : rem);
         unit_end = unit + q + (c < rem ? 1 : 0);
@@ -412,7 +433,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
     constexpr int C = 2 * Q, K = Q / 2;
     constexpr bool BST = MODE == MODE_ADMM && ws_bstage(Q);       // the multiplier is staged by TMA like theta and Phi
     constexpr WsSmem L = ws_smem(Q, BST);
-    constexpr int NF = L.nf;
+    constexpr int NF = L.nf, NRAW = L.nraw;
     static_assert(Q % 2 == 0, "C must be a multiple of 4");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -472,9 +493,10 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
         WsSegIter<R> it(p);
 #pragma unroll 1
         while (it.next()) {
-        const int r0 = it.r0, r1 = it.r1, rs = it.rs, t_end = it.t_end, nblk = it.nblk, b = it.b;
-        const int grp = it.strip * NGRP + gi;
-        const bool grp_live = grp < p.ngroups;
+        const int r0 = it.r0, r1 = it.r1, rs = it.rs, t_end = it.t_end, nblk = it.nblk;
+        const WsSlot sl = ws_slot(p, it.b, it.strip, gi, NGRP);
+        const int b = sl.b, grp = sl.grp;
+        const bool grp_live = sl.live;
         const int base = grp * own - HALO;                          // pixel of lane 0's A
         const int pxa = base + 2 * lane;
         const bool pair_in = grp_live && pxa >= 0 && pxa < W;       // W is even and base is even: pairs are atomic
@@ -618,6 +640,13 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 bool up_ok = p.wait_up == nullptr, dn_ok = p.wait_dn == nullptr;
 #pragma unroll 1
                 while (ld.next()) {
+                    // per group slot of this segment (this lane runs alone: keep its per-block instruction count small)
+                    int l_px0[NGRP], l_row[NGRP], l_prow[NGRP];
+#pragma unroll
+                    for (int g2 = 0; g2 < NGRP; ++g2) {
+                        const WsSlot sl = ws_slot(p, ld.b, ld.strip, g2, NGRP);
+                        l_px0[g2] = sl.grp * own - HALO; l_row[g2] = sl.b * H; l_prow[g2] = p.phi_batched ? sl.b * H : 0;
+                    }
 #pragma unroll 1
                     for (int blk = 0; blk < ld.nblk; ++blk, ++g) {
                         const int slot = g % NRAW;
@@ -629,11 +658,10 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                         // to a seam are pushed into buffers the neighbour read in that iteration: both need its flag.
                         if (!up_ok && row0 < p.out_lo + R) { wait_peer_flag(p.wait_up, p.wait_epoch, p.timeout_flag); up_ok = true; }
                         if (!dn_ok && row0 + WRB > p.out_hi - R) { wait_peer_flag(p.wait_dn, p.wait_epoch, p.timeout_flag); dn_ok = true; }
-                        const int rowc = ld.b * H + row0, prow = (p.phi_batched ? ld.b * H : 0) + row0;
                         mbar_expect_tx(bar, kTx);
 #pragma unroll
                         for (int g2 = 0; g2 < NGRP; ++g2) {
-                            const int px0 = (ld.strip * NGRP + g2) * own - HALO;
+                            const int rowc = l_row[g2] + row0, prow = l_prow[g2] + row0, px0 = l_px0[g2];
                             tma_load_3d(dst + g2 * (WRB * GW * C * 4), &maps.x, 0, px0, rowc, bar);
                             if (TVONLY) continue;
                             tma_load_3d(dst + L.x_bytes + g2 * (WRB * GW * C * 4), &maps.phi, 0, px0, prow, bar);
@@ -650,6 +678,12 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 int g = 0;
 #pragma unroll 1
                 while (st.next()) {
+                    int s_px0[NGRP], s_row[NGRP]; bool s_live[NGRP];
+#pragma unroll
+                    for (int g2 = 0; g2 < NGRP; ++g2) {
+                        const WsSlot sl = ws_slot(p, st.b, st.strip, g2, NGRP);
+                        s_px0[g2] = sl.grp * own; s_row[g2] = sl.b * H; s_live[g2] = sl.live;
+                    }
 #pragma unroll 1
                     for (int blk = 0; blk < st.nblk; ++blk, ++g) {
                         const int os = g % NOUT;
@@ -660,14 +694,16 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                             if (orow >= st.r0 && orow < st.r1) {
                                 const bool to_up = p.sig_up != nullptr && orow < p.out_lo + R;
                                 const bool to_dn = p.sig_dn != nullptr && orow >= p.out_hi - R;
-                                for (int g2 = 0; g2 < NGRP; ++g2)
-                                    if (st.strip * NGRP + g2 < p.ngroups) {
+#pragma unroll
+                                for (int g2 = 0; g2 < NGRP; ++g2) {
+                                    if (s_live[g2]) {
                                         const uint32_t sub = src + (j * NGRP + g2) * L.out_sub;
-                                        const int px0 = (st.strip * NGRP + g2) * own;
-                                        tma_store_4d(&maps.out, sub, 0, px0, 0, st.b * H + orow);
+                                        const int px0 = s_px0[g2];
+                                        tma_store_4d(&maps.out, sub, 0, px0, 0, s_row[g2] + orow);
                                         if (to_up) tma_store_4d(&maps.out_up, sub, 0, px0, 0, orow + p.up_shift);
                                         if (to_dn) tma_store_4d(&maps.out_dn, sub, 0, px0, 0, orow + p.dn_shift);
                                     }
+                                }
                             }
                         }
                         bulk_commit();
@@ -693,8 +729,13 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
 #pragma unroll 1
         while (it.next()) {
         const int r0 = it.r0, r1 = it.r1, rs = it.rs, nblk = it.nblk;
-        const int group0 = it.strip * NGRP;
-        float* y1o = (MODE == MODE_GAP_ACC) ? p.y1_out + (size_t)it.b * H * W : nullptr;
+        // per group slot of this strip: first pixel of the tile, live?, element offset of its measurement plane
+        int s_px0[NGRP]; bool s_live[NGRP]; size_t s_plane[NGRP];
+#pragma unroll
+        for (int g2 = 0; g2 < NGRP; ++g2) {
+            const WsSlot sl = ws_slot(p, it.b, it.strip, g2, NGRP);
+            s_px0[g2] = sl.grp * own - HALO; s_live[g2] = sl.live; s_plane[g2] = (size_t)sl.b * H * W;
+        }
 #pragma unroll 1
         for (int blk = 0; blk < nblk; ++blk, ++gb) {
             const int slot = gb % NRAW, fs = gb % NF;
@@ -710,8 +751,10 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             for (int itx = ptid; itx < NITEM; itx += NPT) {
                 const int px = itx & (GW - 1), g = (itx / GW) % NGRP, j = itx / (GW * NGRP);
                 const int row = rs + blk * WRB + j;
-                const int gpx = (group0 + g) * own - HALO + px;
-                const bool in = (group0 + g) < p.ngroups && gpx >= 0 && gpx < W && row < H;
+                int gpx = s_px0[0] + px; bool live = s_live[0]; size_t plane = s_plane[0];
+#pragma unroll
+                for (int g2 = 1; g2 < NGRP; ++g2) if (g == g2) { gpx = s_px0[g2] + px; live = s_live[g2]; plane = s_plane[g2]; }
+                const bool in = live && gpx >= 0 && gpx < W && row < H;
                 const float4* tx = reinterpret_cast<const float4*>(raw) + ((g * WRB + j) * GW + px) * K;
                 // f tile: [WRB][NGRP][Q][GW][2]
                 float2* frow = reinterpret_cast<float2*>(fdst) + ((j * NGRP + g) * Q) * GW + px;
@@ -731,7 +774,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 for (int k0 = 0; k0 < K; ++k0) { xv[k0] = tx[k0 ^ lsw]; pv[k0] = tp[k0 ^ lsw]; }
                 P2 acc2 = splat(0.f);
                 // ADMM: this pixel's multiplier, C contiguous floats in global memory (zero outside the image)
-                const size_t goff = ADMM ? (((size_t)it.b * H + (row < H ? row : 0)) * W + (in ? gpx : 0)) * C : 0;
+                const size_t goff = ADMM ? (plane + (size_t)(row < H ? row : 0) * W + (in ? gpx : 0)) * C : 0;
                 // staged: the tile next to Phi's (same layout as theta's, so the same chunk order k0 ^ lsw applies)
                 const float4* bsrc = !ADMM ? nullptr : BST ? tx + 2 * (L.x_bytes / 16) : reinterpret_cast<const float4*>(p.b_in + goff);
 #pragma unroll
@@ -753,7 +796,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     const float y1n = sm[NGRP * WRB * GW] + (yv - acc);
                     if (in && px >= HALO && px < HALO + own && row >= r0 && row < r1) {
                         const size_t idx = (size_t)row * W + gpx;
-                        y1o[idx] = y1n;
+                        p.y1_out[plane + idx] = y1n;
                         if (p.y1_up != nullptr && row < p.out_lo + R) p.y1_up[idx] = y1n;
                         if (p.y1_dn != nullptr && row >= p.out_hi - R) p.y1_dn[idx] = y1n;
                     }
