@@ -10,12 +10,13 @@ echo "== gap_tv_ws_kernel<R=4, GAP accelerated, C=24>: fast block of four rows (
 cuobjdump -sass build/ws_inst_r4.o | awk '/Function : .*gap_tv_ws_kernelILi4ELi0ELi12/{f=1} f{print} /Function : .*gap_tv_ws_kernelILi4ELi0ELi4E/{if(f)exit}' | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s+\/\*[0-9a-f]+\*\/\s+(@!?U?P[0-9T]+ )?//' | awk '{print $1}' > /tmp/_k.txt
 python3 - <<'PY'
 ops = [l.strip() for l in open('/tmp/_k.txt')]
-# the fast block: four LDS.128 (one row of f each) with no mbarrier instruction in between, up to the last STS.64 of the fourth row
+# the fast block: eight LDS.128 (f(t) and f(t-R) of four rows) with no mbarrier instruction in between, up to the last STS.64 of the fourth row
 for i, o in enumerate(ops):
     if o.startswith('LDS.128'):
-        idx = [k for k in range(i, min(i + 1200, len(ops))) if ops[k].startswith('LDS.128')][:4]
-        if len(idx) == 4 and not any(x.startswith('SYNCS') or x.startswith('BAR') for x in ops[i:idx[3]]):
-            end = max(k for k in range(idx[3], min(idx[3] + 400, len(ops))) if ops[k].startswith('STS'))
+        idx = [k for k in range(i, min(i + 1200, len(ops))) if ops[k].startswith('LDS.128')][:8]
+        if len(idx) == 8 and not any(x.startswith('SYNCS') or x.startswith('BAR') for x in ops[i:idx[7]]):
+            stop = next((k for k in range(idx[7], min(idx[7] + 400, len(ops))) if ops[k].startswith('SYNCS') or ops[k].startswith('BAR')), idx[7] + 400)
+            end = max(k for k in range(idx[7], stop) if ops[k].startswith('STS'))
             blk = ops[i:end + 1]
             from collections import Counter
             c = Counter(x.split('.')[0] for x in blk)
