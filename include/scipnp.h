@@ -278,10 +278,10 @@ int scipnp_solver_uses_fused(scipnp_solver *s);
 /* --------------------------------------------------------------------------
  * Row-tiled multi-GPU mode (one process per GPU on one node; no counterpart in
  * the single-process reference).  The handle holds rows [row_lo, row_hi) of a
- * taller scene (so p.H = row_hi - row_lo, B = 1, GAP) and owns [lo, hi); the
+ * taller scene (so p.H = row_hi - row_lo, B = 1; GAP or ADMM) and owns [lo, hi); the
  * other rows are halo copies of rows owned by the neighbouring ranks.  The
  * neighbours' buffers are mapped with CUDA IPC; an exchange pulls the halo rows
- * of x and y1 straight over NVLink, ordered by flags the ranks write into each
+ * of x and y1 (ADMM: theta and the multiplier b) straight over NVLink, ordered by flags the ranks write into each
  * other's memory (no host round trip, no collective):
  *   _tiling        declare the row ranges of this rank
  *   _ipc_export    blob (scipnp_solver_ipc_blob_bytes() bytes) describing my buffers

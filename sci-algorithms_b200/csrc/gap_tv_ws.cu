@@ -216,6 +216,11 @@ int launch_fused_ws(const FusedArgs& a, cudaStream_t st) {
             p.y1_dn = t.y1_dn ? t.y1_dn + (long long)t.dn_shift * a.W : nullptr;
             if ((t.x_up && !t.y1_up) || (t.x_dn && !t.y1_dn)) { set_error("halo push: accelerated GAP needs the neighbours' y1"); return SCIPNP_EINVAL; }
         }
+        if (a.mode == MODE_ADMM) {
+            p.b_up = t.b_up ? t.b_up + (long long)t.up_shift * a.W * a.C : nullptr;
+            p.b_dn = t.b_dn ? t.b_dn + (long long)t.dn_shift * a.W * a.C : nullptr;
+            if ((t.x_up && !t.b_up) || (t.x_dn && !t.b_dn)) { set_error("halo push: ADMM needs the neighbours' multiplier"); return SCIPNP_EINVAL; }
+        }
         p.wait_up = t.x_up ? t.wait_up : nullptr; p.wait_dn = t.x_dn ? t.wait_dn : nullptr;
         p.sig_up = t.x_up ? t.sig_up : nullptr; p.sig_dn = t.x_dn ? t.sig_dn : nullptr;
         p.wait_epoch = t.wait_epoch; p.sig_epoch = t.sig_epoch;

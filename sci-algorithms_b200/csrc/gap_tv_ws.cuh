@@ -97,6 +97,7 @@ struct WsParams {
     // the last CTA raises the neighbours' flags to sig_epoch; the loader lane waits for my flags to reach wait_epoch
     // before it touches a block that holds halo rows or the owned rows next to them.
     float* y1_up; float* y1_dn;   // the neighbours' y1_out, shifted so that my local (row, px) index applies
+    float* b_up; float* b_dn;     // ADMM: the neighbours' b_out, shifted likewise
     int up_shift, dn_shift;       // my local row + shift = the neighbour's local row (TMA store coordinate)
     const int* wait_up; const int* wait_dn;
     int* sig_up; int* sig_dn;
@@ -536,9 +537,18 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
             // consumer warps complete the sectors in L2).
             auto store_b = [&](int orow, const P2 (&o)[2], const P2 (&fo)[2], bool check_rows) {
                 if (!own_lane || (check_rows && (orow < r0 || orow >= r1))) return;
-                float* dst = p.b_out + (((size_t)b * H + orow) * W + pxa) * C + 2 * q;
-                *reinterpret_cast<float2*>(dst) = make_float2(o[0].x - fo[0].x, o[0].y - fo[0].y);
-                *reinterpret_cast<float2*>(dst + C) = make_float2(o[1].x - fo[1].x, o[1].y - fo[1].y);
+                const size_t off = (((size_t)b * H + orow) * W + pxa) * C + 2 * q;
+                const float2 ba = make_float2(o[0].x - fo[0].x, o[0].y - fo[0].y), bb = make_float2(o[1].x - fo[1].x, o[1].y - fo[1].y);
+                *reinterpret_cast<float2*>(p.b_out + off) = ba;
+                *reinterpret_cast<float2*>(p.b_out + off + C) = bb;
+                if (p.b_up != nullptr && orow < p.out_lo + R) {          // halo push: the rows next to a seam, into the neighbours' halo rows
+                    *reinterpret_cast<float2*>(p.b_up + off) = ba;
+                    *reinterpret_cast<float2*>(p.b_up + off + C) = bb;
+                }
+                if (p.b_dn != nullptr && orow >= p.out_hi - R) {
+                    *reinterpret_cast<float2*>(p.b_dn + off) = ba;
+                    *reinterpret_cast<float2*>(p.b_dn + off + C) = bb;
+                }
             };
             auto fast_block = [&](auto path) {
                 constexpr int PATH = decltype(path)::value;
@@ -617,6 +627,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 }
         }
         }   // segments
+        if (MODE == MODE_ADMM && (p.b_up != nullptr || p.b_dn != nullptr)) __threadfence_system();   // pushed b rows before the flag
         if (p.prof && lane == 0) {
             long long* pr = p.prof + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * 4;
             pr[0] = clock64() - pstart; pr[1] = pw0; pr[2] = pw1; pr[3] = 0;
@@ -781,7 +792,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                 for (int k0 = 0; k0 < K; ++k0) {
                     float4 u = xv[k0];
                     if (ADMM && in) {                                // u = theta + b enters the dot product
-                        const float4 bq = BST ? bsrc[k0 ^ lsw] : __ldg(bsrc + (k0 ^ lsw));
+                        const float4 bq = BST ? bsrc[k0 ^ lsw] : __ldcg(bsrc + (k0 ^ lsw));     // L2: halo rows are written by other GPUs
                         u.x += bq.x; u.y += bq.y; u.z += bq.z; u.w += bq.w;
                     }
                     acc2 = fma2(make_float2(u.x, u.y), make_float2(pv[k0].x, pv[k0].y), acc2);
@@ -816,7 +827,7 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
                     frow[(2 * kc) * GW] = f01;                       // TV input: f = theta + lambda*s*Phi = x - b
                     frow[(2 * kc + 1) * GW] = f23;
                     if (ADMM && want_x) {                            // x = f + b (the projection output the caller reads)
-                        const float4 bq = BST ? bsrc[kc] : __ldg(bsrc + kc);
+                        const float4 bq = BST ? bsrc[kc] : __ldcg(bsrc + kc);
                         reinterpret_cast<float4*>(p.xproj_out + goff)[kc] = make_float4(f01.x + bq.x, f01.y + bq.y, f23.x + bq.z, f23.y + bq.w);
                     }
                 }

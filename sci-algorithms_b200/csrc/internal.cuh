@@ -67,6 +67,7 @@ struct FusedArgs {
 struct TilePush {
     float* x_up = nullptr; float* x_dn = nullptr;         // neighbour's x_out (null: no neighbour on that side)
     float* y1_up = nullptr; float* y1_dn = nullptr;       // neighbour's y1_out (accelerated GAP)
+    float* b_up = nullptr; float* b_dn = nullptr;         // neighbour's b_out (ADMM)
     int up_rows = 0, dn_rows = 0;                         // local rows of the neighbours' buffers
     int up_shift = 0, dn_shift = 0;                       // my local row + shift = the neighbour's local row
     const int* wait_up = nullptr; const int* wait_dn = nullptr;

@@ -155,7 +155,8 @@ int scipnp_solver_create(const scipnp_params* pp, scipnp_solver** out) {
         DM(s->fws, s->fws_bytes, char);
     }
     s->xbuf[0] = s->xa; s->xbuf[1] = s->xb;
-    s->y1buf[0] = s->y1a; s->y1buf[1] = s->y1b;
+    // the second carried array of the iteration: y1 (accelerated GAP) or the multiplier b (ADMM)
+    s->y1buf[0] = p.method == 0 ? s->y1a : s->ba; s->y1buf[1] = p.method == 0 ? s->y1b : s->bb;
     // exact-path workspace is allocated lazily (only the exact path or a rollback needs it)
     s->launches0 = g_launches.load();
     *out = s;
@@ -285,7 +286,8 @@ static int step_exact(scipnp_solver* s, int k, cudaStream_t st) {
                                    s->phi, s->PhiSum, p.lambda, p.gamma, p.B, p.H, p.W, p.C,
                                    p.phi_batched, st)) return e;
         if (int e = tv_chambolle_exact(s->fbuf, s->xa, p.tv_weight, p.tv_eps, p.tv_iter_max, p.B, p.H,
-                                       p.W, p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st)) return e;
+                                       p.W, p.C, s->tvws, s->tvws_bytes, nullptr, nullptr, 0, st,
+                                       s->tiled && s->tv_tiling.reduce ? &s->tv_tiling : nullptr)) return e;
         if (p.clip01) if (int e = launch_clip01(s->xa, s->n_frame, st)) return e;
         if (int e = scipnp_admm_dual_update(s->ba, s->xproj, s->xa, s->n_frame, st)) return e;
         if (int e = record_sqerr(s, k, s->xproj, st)) return e;
@@ -332,14 +334,19 @@ static int step_fused(scipnp_solver* s, int k, bool last, cudaStream_t st) {
         }
     }
     if (push) {
-        const int xo = s->xb == s->xbuf[0] ? 0 : 1, yo = s->y1b == s->y1buf[0] ? 0 : 1;
+        const bool admm = p.method == 1;
+        const int xo = s->xb == s->xbuf[0] ? 0 : 1, yo = (admm ? s->bb : s->y1b) == s->y1buf[0] ? 0 : 1;
         if (s->up.present) {
-            tp.x_up = s->up.x[xo]; tp.y1_up = p.accelerate ? s->up.y1[yo] : nullptr;
+            tp.x_up = s->up.x[xo];
+            tp.y1_up = (!admm && p.accelerate) ? s->up.y1[yo] : nullptr;
+            tp.b_up = admm ? s->up.y1[yo] : nullptr;
             tp.up_rows = s->up.rows; tp.up_shift = s->t_row_lo - s->up.row_lo;
             tp.wait_up = s->sync + 8; tp.sig_up = s->up.sync + 9;
         }
         if (s->dn.present) {
-            tp.x_dn = s->dn.x[xo]; tp.y1_dn = p.accelerate ? s->dn.y1[yo] : nullptr;
+            tp.x_dn = s->dn.x[xo];
+            tp.y1_dn = (!admm && p.accelerate) ? s->dn.y1[yo] : nullptr;
+            tp.b_dn = admm ? s->dn.y1[yo] : nullptr;
             tp.dn_rows = s->dn.rows; tp.dn_shift = s->t_row_lo - s->dn.row_lo;
             tp.wait_dn = s->sync + 9; tp.sig_dn = s->dn.sync + 8;
         }
@@ -632,7 +639,7 @@ int scipnp_solver_ipc_blob_bytes(void) { return kIpcBlob; }
 
 int scipnp_solver_tiling(scipnp_solver* s, int lo, int hi, int row_lo, int row_hi) {
     SCIPNP_REQUIRE(s, "null solver");
-    SCIPNP_REQUIRE(s->p.B == 1 && s->p.method == 0, "tiling covers a single GAP scene (B = 1)");
+    SCIPNP_REQUIRE(s->p.B == 1, "tiling covers a single scene (B = 1)");
     SCIPNP_REQUIRE(row_lo <= lo && lo < hi && hi <= row_hi && row_hi - row_lo == s->p.H, "inconsistent row ranges");
     s->t_lo = lo; s->t_hi = hi; s->t_row_lo = row_lo; s->t_row_hi = row_hi;
     if (!s->sync) {
@@ -712,10 +719,13 @@ int scipnp_solver_exchange(scipnp_solver* s, void* stream) {
     const int e = ++s->epoch;
     const int W = s->p.W, C = s->p.C;
     const int xi = s->xa == s->xbuf[0] ? 0 : 1;
-    const int yi = s->y1a == s->y1buf[0] ? 0 : 1;
+    const bool admm = s->p.method == 1;
+    float* aux = admm ? s->ba : s->y1a;                       // the second carried array: y1 (GAP) or b (ADMM)
+    const bool has_aux = admm || s->p.accelerate;
+    const int yi = aux == s->y1buf[0] ? 0 : 1;
     // one launch: announce my rows (I am the upper neighbour's "down" side), wait for theirs,
     // pull my halo rows out of their owned rows, acknowledge
-    const size_t rowx = (size_t)W * C, rowy = (size_t)W;
+    const size_t rowx = (size_t)W * C, rowy = admm ? rowx : (size_t)W;
     PullJob j{};
     int nr = 0;
     long long total4 = 0;
@@ -731,14 +741,14 @@ int scipnp_solver_exchange(scipnp_solver* s, void* stream) {
         const int n = s->t_lo - s->t_row_lo, src = s->t_row_lo - s->up.row_lo;
         if (n > 0) {
             add(s->up.x[xi] + src * rowx, s->xa, n * rowx);
-            if (s->p.accelerate && s->up.y1[yi]) add(s->up.y1[yi] + src * rowy, s->y1a, n * rowy);
+            if (has_aux && s->up.y1[yi]) add(s->up.y1[yi] + src * rowy, aux, n * rowy);
         }
     }
     if (s->dn.present) {
         const int n = s->t_row_hi - s->t_hi, dst = s->t_hi - s->t_row_lo, src = s->t_hi - s->dn.row_lo;
         if (n > 0) {
             add(s->dn.x[xi] + src * rowx, s->xa + dst * rowx, n * rowx);
-            if (s->p.accelerate && s->dn.y1[yi]) add(s->dn.y1[yi] + src * rowy, s->y1a + dst * rowy, n * rowy);
+            if (has_aux && s->dn.y1[yi]) add(s->dn.y1[yi] + src * rowy, aux + dst * rowy, n * rowy);
         }
     }
     j.ready_up = s->up.present ? s->up.sync + 1 : nullptr;
@@ -804,11 +814,12 @@ int scipnp_solver_enable_push(scipnp_solver* s, int up_rows, int dn_rows) {
     const scipnp_params& p = s->p;
     const int R = p.tv_iter_max - 1;
     FusedArgs a{};
-    a.mode = p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN;
-    a.B = p.B; a.H = p.H; a.W = p.W; a.C = p.C; a.tv_iter_max = p.tv_iter_max;
+    a.mode = p.method == 1 ? MODE_ADMM : (p.accelerate ? MODE_GAP_ACC : MODE_GAP_PLAIN);
+    a.B = p.B; a.H = p.H; a.W = p.W; a.C = p.C; a.tv_iter_max = p.tv_iter_max; a.clip01 = p.clip01;
     a.x_in = s->xa; a.x_out = s->xb; a.Phi = s->Phi; a.y = s->y; a.Phi_sum = s->PhiSum; a.y1_in = s->y1a; a.y1_out = s->y1b;
+    a.b_in = s->ba; a.b_out = s->bb; a.xproj_out = s->xproj;
     if (!s->fused_possible || !s->xb || !fused_ws_supported(a)) {
-        set_error("halo push needs the warp-specialised fused kernel (GAP, C %% 4 == 0, C <= 24, W %% 4 == 0)");
+        set_error("halo push needs the warp-specialised fused kernel (GAP or ADMM without clip, C %% 4 == 0, C <= 24, W %% 4 == 0)");
         return SCIPNP_ESTATE;
     }
     if ((s->up.present && (s->t_lo - s->t_row_lo != R || up_rows < 1)) ||

@@ -89,17 +89,18 @@ def _wrap(ptr, shape, device, typestr="<f4"):
 
 
 class TiledSolver:
-    """One rank of the row-tiled GAP-TV solver (accelerated GAP, TV prior)."""
+    """One rank of the row-tiled GAP-TV / ADMM-TV solver (TV prior)."""
 
     def __init__(self, H, W, C, rank, world, tv_weight=0.1, tv_iter_max=5, _lambda=1.0,
                  accelerate=True, exchange_every=1, group=None, fused=True, transport="nccl",
-                 tv_eps=2.e-4, method="gap"):
+                 tv_eps=2.e-4, method="gap", gamma=0.01):
         """transport: "nccl" (send/recv pairs through torch.distributed), "p2p" (CUDA-IPC
         mapped neighbour buffers, halo rows pulled over NVLink by the library, device-side
         flags) or "auto" (p2p when every rank can set it up, else nccl)."""
         from .engine import Solver
-        if str(method).lower() != "gap":
-            raise NotImplementedError("the row-tiled mode runs GAP-TV (ADMM-TV scenes are sharded per measurement)")
+        self.method = str(method).lower()
+        if self.method not in ("gap", "admm"):
+            raise ValueError("method must be 'gap' or 'admm'")
         self.H, self.W, self.C = H, W, C
         self.rank, self.world, self.group = rank, world, group
         self.k = max(1, int(exchange_every))
@@ -107,8 +108,8 @@ class TiledSolver:
         self.lo, self.hi, self.row_lo, self.row_hi = partition_rows(H, world, rank, self.halo)
         self.local_rows = self.row_hi - self.row_lo
         self.accelerate = accelerate
-        self.solver = Solver(1, self.local_rows, W, C, method="gap", accelerate=accelerate,
-                             _lambda=_lambda, tv_weight=tv_weight, tv_iter_max=tv_iter_max,
+        self.solver = Solver(1, self.local_rows, W, C, method=self.method, accelerate=accelerate,
+                             _lambda=_lambda, gamma=gamma, tv_weight=tv_weight, tv_iter_max=tv_iter_max,
                              tv_eps=tv_eps, fused=fused)
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.exchanges = 0
@@ -195,11 +196,22 @@ class TiledSolver:
                          X_orig=None if X_orig_local is None else X_orig_local[None], borrow_phi=borrow_phi)
 
     def _fields(self):
+        """The carried arrays of the iteration as tensors over the solver's buffers: x and y1 (accelerated GAP), or
+        theta and the multiplier b (ADMM)."""
         xp, y1p = self.solver.state_ptrs()
         f = [_wrap(xp, (self.local_rows, self.W, self.C), self.device)]
-        if self.accelerate:
+        if self.method == "admm":
+            f.append(_wrap(y1p, (self.local_rows, self.W, self.C), self.device))
+        elif self.accelerate:
             f.append(_wrap(y1p, (self.local_rows, self.W), self.device))
         return f
+
+    def _result_field(self):
+        """What the reference returns: x for GAP, the projection output x (not theta) for ADMM
+        (pnp_sci_algo.py:840,864)."""
+        if self.method != "admm":
+            return self._fields()[0]
+        return _wrap(self.solver.admm_state_ptrs()[2], (self.local_rows, self.W, self.C), self.device)
 
     def _sweep(self, iters):
         if self.transport == "p2p":
@@ -289,7 +301,7 @@ class TiledSolver:
 
     def owned(self, out=None):
         """Owned rows of the current estimate as a device tensor [hi-lo, W, C]."""
-        x = self._fields()[0]
+        x = self._result_field()
         res = x[self.lo - self.row_lo:self.hi - self.row_lo]
         if out is not None:
             out.copy_(res)

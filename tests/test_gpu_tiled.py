@@ -93,6 +93,20 @@ def test_push_tiled_shapes(sp, tmp_path, world, H, W, C, T):
     assert float(np.abs(got - ref).max()) <= 1e-6
 
 
+@pytest.mark.parametrize("world,H,W,C,k,fused", [(2, 72, 128, 8, 1, True), (3, 100, 192, 24, 1, True), (2, 72, 128, 8, 2, True),
+                                                  (2, 72, 128, 12, 1, False)])
+def test_tiled_admm_equals_single_gpu(sp, tmp_path, world, H, W, C, k, fused):
+    """ADMM-TV over row tiles: theta and the multiplier b are the carried arrays (the seam rows of both are pushed by
+    the fused kernel at k = 1 -- b by plain peer stores of the consumers, staged by TMA at C = 8, read from global
+    memory at C = 24 -- and pulled by the exchange kernel otherwise); the result is x, the projection output."""
+    iters = 6
+    got, meta = _tiled(tmp_path, world, H, W, C, iters, k, fused=fused, method="admm")
+    ref, refined = _single(H, W, C, iters, fused=fused, method="admm")
+    assert refined == 0 and (meta[:, 1] == (1 if fused else 0)).all()
+    assert (meta[:, 2] == (1 if (fused and k == 1) else 0)).all()
+    assert float(np.abs(got - ref).max()) <= (1e-6 if fused else 0.0)
+
+
 def test_push_tiled_rollback_whole_scene_rule(sp, tmp_path):
     """k = 1 (push) with an eps at which skimage's rule fires: the decision is taken on the energies of the whole
     scene (the per-iteration log summed over the ranks), every rank rolls back, the exact path (pull exchange)

@@ -1,0 +1,2 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_tiled.py -x -q 2>&1 | tail -12
