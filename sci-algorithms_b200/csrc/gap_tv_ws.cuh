@@ -49,6 +49,9 @@ using namespace fusedk;     // PTX helpers, P2 arithmetic
 #ifndef WS_PROD_FIRST
 #define WS_PROD_FIRST 0   // 1: the producer-side warps take warp ids 0..3 and the consumers 4..: the arbiter prefers high warp
 #endif                    // ids, so the consumers (the bottleneck) win ties and the producers fill the gaps
+#ifndef WS_BLK_UNROLL
+#define WS_BLK_UNROLL 1   // unroll factor of the consumers' block loop (2: +0 %, not used)
+#endif
 #ifndef WS_SANITIZE
 #define WS_SANITIZE 0     // 1: every lane arrives on the mbarriers (counts x 32) instead of one elected lane behind a __syncwarp:
 #endif                    // same protocol, but visible thread by thread to compute-sanitizer's racecheck (tools/sanitize.sh)
@@ -515,7 +518,11 @@ gap_tv_ws_kernel(const WsParams p, const __grid_constant__ WsMaps maps) {
         sc.right_in = (pair_in && pxa + 2 < W) ? 1.f : 0.f;
         sc.rs = rs; sc.r0 = r0; sc.r1 = r1;
         const int fast_lo = r0 + R, fast_hi = min(r1, H) - 1;
+#if WS_BLK_UNROLL == 2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int blk = 0; blk < nblk; ++blk, ++gb) {
             const int fs = gb % NF, os = gb % NOUT;
             long long c0 = 0, c1 = 0;

@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+E=$PWD/sci-algorithms_b200/build/exp
+for i in 1 2; do
+echo "main: $(timeout 200 python profiles/prof_driver.py 40 2>&1 | tail -1)"
+echo "blk2: $(SCIPNP_LIB=$E/libscipnp_blk2.so timeout 200 python profiles/prof_driver.py 40 2>&1 | tail -1)"
+done

@@ -15,19 +15,22 @@ from scipnp import synth  # noqa: E402
 from scipnp.engine import Solver  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-cases = [("gap", 72, 128, 8, True), ("gap", 40, 64, 24, False), ("admm", 48, 64, 8, True)]
-for method, H, W, C, acc in cases:
+# (method, B, H, W, C, accelerated): one scene; a batch of three whose groups are packed across the measurements; plain GAP
+# at C = 24; ADMM with the multiplier staged by TMA (C = 8) and read from global memory (C = 24)
+cases = [("gap", 1, 72, 128, 8, True), ("gap", 3, 40, 128, 8, True), ("gap", 1, 40, 64, 24, False),
+         ("admm", 1, 48, 64, 8, True), ("admm", 1, 40, 64, 24, True)]
+for method, B, H, W, C, acc in cases:
     if which not in ("all", method):
         continue
-    meas, mask, _ = synth.make_cacti(H, W, C, 1, cfg=5)
-    y = meas[:, :, 0] / np.float32(255.)
+    meas, mask, _ = synth.make_cacti(H, W, C, B, cfg=5)
+    y = np.ascontiguousarray(np.moveaxis(meas, 2, 0)) / np.float32(255.)
     out = []
     for fused in (True, False):
-        with Solver(1, H, W, C, method=method, accelerate=acc, tv_weight=0.3, tv_iter_max=5, fused=fused) as s:
-            s.load(y[None], mask)
+        with Solver(B, H, W, C, method=method, accelerate=acc, tv_weight=0.3, tv_iter_max=5, fused=fused) as s:
+            s.load(y, mask)
             s.run(2)
-            out.append(s.get_x()[0])
-    print("%s %dx%dx%d acc=%s: max|fused - exact| = %.3g" % (method, H, W, C, acc, float(np.abs(out[0] - out[1]).max())))
+            out.append(s.get_x())
+    print("%s %dx%dx%dx%d acc=%s: max|fused - exact| = %.3g" % (method, B, H, W, C, acc, float(np.abs(out[0] - out[1]).max())))
 if which in ("all", "tv"):
     f = torch.rand((48, 64, 8), device="cuda")
     a = scipnp.denoise_tv_chambolle(f, 0.3, n_iter_max=5, multichannel=True)
