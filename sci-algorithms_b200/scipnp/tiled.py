@@ -18,7 +18,16 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["partition_rows", "exchange_halos", "TiledSolver", "tiled_reference_run", "gap_denoise_tiled"]
+__all__ = ["partition_rows", "exchange_halos", "TiledSolver", "tiled_reference_run", "gap_denoise_tiled",
+           "stop_rule_hits"]
+
+
+def stop_rule_hits(energy, eps):
+    """skimage's stopping test of ``denoise_tv_chambolle`` on logged energies ``[..., n_dual]`` (one row per outer
+    iteration and channel slice): true where ``|E_{i-1} - E_i| < eps * E_0`` for some dual iteration ``i >= 1`` -- a
+    stop at the last executed iteration changes nothing, so the last column is only compared as ``E_i``."""
+    e = energy
+    return ((e[..., :-1] - e[..., 1:]).abs() < eps * e[..., 0:1]).any(dim=-1)
 
 
 def partition_rows(H, world, rank, halo):
@@ -283,7 +292,7 @@ class TiledSolver:
         res = buf[-2:]
         if have:
             e = buf[:-2].reshape(n.value, per.value // self.R, self.R)
-            hit = ((e[..., :-1] - e[..., 1:]).abs() < self.tv_eps * e[..., 0:1]).any().to(torch.float64).reshape(1)
+            hit = stop_rule_hits(e, self.tv_eps).any().to(torch.float64).reshape(1)
             res = torch.cat([res, hit])
         res = res.tolist()               # the one host synchronisation of the run
         if res[1] > 0:

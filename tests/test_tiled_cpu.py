@@ -135,3 +135,30 @@ def test_sharded_measurements_equal_single_process(tmp_path):
         np.testing.assert_array_equal(np.load(tmp_path / ("pa_%d.npy" % r)), np.array(ref[4]))
     assert shard_indices(5, 2, 0) == [0, 2, 4] and shard_indices(5, 2, 1) == [1, 3]
     assert sorted(shard_indices(28, 8, 3)) == [3, 11, 19, 27]
+
+
+def test_whole_scene_stop_rule_on_logged_energies():
+    """The tiled driver sums the per-rank energy logs and replays skimage's eps test (oracle/tv_chambolle.py: the
+    loop breaks at dual iteration i >= 1 when |E_{i-1} - E_i| < eps * E_0).  The replay must take the oracle's
+    decision: against the oracle's own executed-iteration count, on scenes where the rule fires and where it does
+    not.  (A stop at the last iteration returns the same image and is not reported.)"""
+    import torch
+    from scipnp.tiled import stop_rule_hits
+    from oracle.tv_chambolle import denoise_tv_chambolle
+    rng = np.random.default_rng(4)
+    img = rng.random((24, 20, 3)).astype(np.float32)
+    img[:, :, 2] = 0.5 + 0.01 * img[:, :, 2]              # a nearly flat slice: its energies settle at once
+    T = 5
+    full = []
+    denoise_tv_chambolle(img, 0.3, eps=0.0, n_iter_max=T, multichannel=True, energy_out=full)
+    assert all(len(e) == T for e in full)
+    logged = torch.tensor(np.array(full)[:, :T - 1], dtype=torch.float64)      # what the fused kernel logs: E_0 .. E_{T-2}
+    seen = set()
+    for eps in (0.9, 0.3, 0.05, 2e-4, 1e-7):
+        got = []
+        denoise_tv_chambolle(img, 0.3, eps=eps, n_iter_max=T, multichannel=True, energy_out=got)
+        stopped_early = [len(e) <= T - 1 for e in got]                          # broke at some i <= T-2
+        fired = stop_rule_hits(logged, eps).tolist()
+        assert fired == stopped_early, (eps, fired, stopped_early)
+        seen.update(stopped_early)
+    assert seen == {True, False}
