@@ -51,11 +51,6 @@ struct FusedArgs {
     // CASSI: Phi == nullptr and the coded aperture mask2d [H][mask_w] is read at offset step*c
     const float* mask2d; int cassi_step; int mask_w;
     int clip01;               // clip the TV output to [0,1]
-    // Row-tiled scenes: only rows [e_lo, e_hi) (the rows this rank owns) enter the TV energies, which the caller
-    // sums over the ranks before it applies the stopping rule.  e_hi == 0: every row.
-    int e_lo = 0, e_hi = 0;
-    bool accumulate_only = false;   // leave the energies in the workspace: no check, no reset (flag is ignored)
-    bool skip_clear = false;        // the workspace slot is already zero
     // Warp-specialised kernel only: produce rows [out_lo, out_hi) of the H local rows (out_hi == 0: all of them), keep
     // this launch's [B][C][R] energies in energy_log, push the rows next to a tile seam to the neighbours (TilePush).
     int out_lo = 0, out_hi = 0;
