@@ -7,7 +7,7 @@
 //     into the TV input f = x + lambda*s*Phi (one thread per (row, pixel): the whole dot product over
 //     the C channels, the y1 update, the scale, f for every channel) and leave f in shared memory in a
 //     channel-pair-major layout.  CONSUMER warps run the Chambolle pipeline on f and never touch the
-//     projection.  One STORER lane hands finished rows to the TMA unit.  The roles are coupled only
+//     projection.  One TMA warp: lane 0 issues every load, lane 1 every store.  The roles are coupled only
 //     through mbarrier rings (raw tiles, f tiles, output tiles), so no warp waits for a CTA-wide barrier.
 //   * A consumer lane owns two horizontally adjacent pixels x one channel pair (4 values, two packed
 //     float2 chains): a warp covers 64 pixels of one channel pair.  Half of the horizontal neighbours
@@ -15,9 +15,17 @@
 //     group is 4 pixels = 2 lanes per side, i.e. up to 56 of 64 pixels are owned (24 of 32 before).
 //   * Output rows are assembled in a chunk-major shared-memory tile ([C/4][own][4]) and written with TMA
 //     tensor stores of exactly the owned pixels; y1 is written by the producers (coalesced).
-//   * One CTA per SM, one row segment per CTA: grid = batch x column strips x row segments, strips and
-//     segments chosen on the host so that the grid is one full wave and neighbouring strips walk down
-//     the image in lockstep (the halo columns they share then come out of L2, not DRAM).
+//   * One CTA per SM.  The scene is (batch x column strips) laid end to end in ticks (a row of an interior strip 16, a
+//     row of the first / last strip 17: their blocks carry pixel masks; every strip charged 8 rows for starting a row
+//     segment) and every CTA takes the same number of consecutive ticks (WsSegIter): one to three row segments per
+//     CTA, no wave quantisation.  With several measurements whose groups do not fill the strips, the groups of all
+//     measurements are laid end to end (ws_slot).  The two TMA lanes run alone in their warp: whatever does not depend
+//     on the block is computed once per segment.
+//   * Modes: accelerated / plain GAP, ADMM (the multiplier staged by TMA where shared memory allows, else read by the
+//     projection threads; b_new = theta_new - f written by the consumers), the TV denoiser alone.  Ring depths per
+//     channel count (ws_smem): 2-3 raw slots, 2-4 f slots, 2 output slots; 8 consumer warps for C <= 8, else 12.
+//   * Row-tiled multi-GPU mode: output row window, seam rows stored a second time into the neighbours' buffers (TMA
+//     stores / plain peer stores over NVLink), flags raised by the last CTA and awaited by the loader lane.
 //
 // Dual-iteration pipeline of a consumer (row streaming, one-row lag per dual iteration), per step t:
 //   stage i (0..R-1) receives out_i(t-i), advances the dual variable of row u = t-i-1 and emits

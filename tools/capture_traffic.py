@@ -10,6 +10,7 @@ import glob
 import hashlib
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -19,12 +20,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KERNEL_SOURCES = ("gap_tv_ws.cuh", "gap_tv_stream.cuh", "ws_inst_r4.cu")     # the device code of the measured kernel
 
 
+def _code_only(text):
+    """C++ source without comments and whitespace: the stamp follows the code, not its commentary."""
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    return re.sub(r"\s+", "", text)
+
+
 def source_hash():
     h = hashlib.sha256()
     for name in KERNEL_SOURCES:
         p = os.path.join(ROOT, "sci-algorithms_b200", "csrc", name)
         h.update(name.encode())
-        h.update(open(p, "rb").read())
+        h.update(_code_only(open(p).read()).encode())
     return h.hexdigest()[:16]
 
 
