@@ -193,3 +193,23 @@ def test_matlab_fgp_first_iterate_is_the_input_and_weights_follow_the_t_sequence
     y = _frames((10, 12, 3))
     for name in ("fgp_denoise_ATV2D", "fgp_denoise_ITV2D", "fgp_denoise_ITV3D"):
         np.testing.assert_array_equal(getattr(M, name)(y, 0.1, 1), y)
+
+
+def test_independent_restatements_agree_on_the_minimisers():
+    """Mutual corroboration of the unpinned restatements: run to convergence, algorithms of different families that
+    minimise the same functional must meet.  Anisotropic ROF (1/2|u-f|^2 + w*TV_aniso): the iterative-clipping
+    ATV_ClipB (TV_denoising_clip_LB.m) and the fast gradient projection ATV_FGP (fgp_denoise_ATV2D.m).  Isotropic
+    ROF with the same weight: scikit-image's Chambolle iteration (oracle/tv_chambolle.py, R6) and ITV2D_FGP
+    (fgp_denoise_ITV2D.m) -- two code bases, two boundary treatments, one minimiser."""
+    from oracle import matlab_tv as M
+    from oracle.tv_chambolle import denoise_tv_chambolle
+    rng = np.random.default_rng(1)
+    f = rng.random((24, 28, 2))
+    w = 0.15
+    atv_fgp = M.fgp_denoise_ATV2D(f, w, 400)
+    assert np.abs(M.TV_denoising_clip_LB(f, w, 2000) - atv_fgp).max() < 1e-4
+    itv_fgp = M.fgp_denoise_ITV2D(f, w, 400)
+    sk = denoise_tv_chambolle(f, weight=w, eps=0.0, n_iter_max=3000, multichannel=True)
+    assert np.abs(sk - itv_fgp).max() < 2e-3
+    # and the two functionals are different problems: the check above is not vacuous
+    assert np.abs(atv_fgp - itv_fgp).max() > 1e-2
